@@ -1,0 +1,558 @@
+// Data-movement, small elementwise / reduction stages, parameter layout preparation and the fused
+// clip-grad-norm + Adam step of the gail-carla hot path (sm_100a).  Entry points documented in
+// include/gail_carla_b200.h; all of these are HBM-bound or tiny.
+#include <algorithm>
+
+#include "gc_common.cuh"
+#include "../../include/gail_carla_b200.h"
+
+namespace {
+
+constexpr int kObsC = 3, kObsH = 192, kObsW = 192;
+constexpr int kS2dH = 96, kS2dW = 96, kS2dC = 16;
+constexpr int kFeat = 25600, kPix = 100, kC4 = 256;
+__constant__ float c_mean[3] = {0.485f, 0.456f, 0.406f};  // tools/model.py:154
+__constant__ float c_std[3] = {0.229f, 0.224f, 0.225f};   // tools/model.py:155
+
+inline int grid_for(long n, int threads, int per_sm) {
+  return (int)std::max<long>(1, std::min<long>((n + threads - 1) / threads, (long)per_sm * gc::kNumSMs));
+}
+
+// ---- image gather: CHW fp32 storage row -> normalised space-to-depth NHWC tile -----------------------------
+// One CTA per (sample, s2d row Y): stage 3 channels x 2 rows x 192 floats in smem (coalesced reads), then write
+// the 96 x 16 = 1536 output floats of that row contiguously.
+__global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+                                                             float* __restrict__ out) {
+  __shared__ float tile[kObsC][2][kObsW + 1];
+  const int b = blockIdx.y, Y = blockIdx.x;
+  const long row = idx ? idx[b] : b;
+  const float* s = src + row * (long)(kObsC * kObsH * kObsW);
+  for (int i = threadIdx.x; i < kObsC * 2 * kObsW; i += blockDim.x) {
+    const int x = i % kObsW, dy = (i / kObsW) % 2, c = i / (2 * kObsW);
+    tile[c][dy][x] = (__ldg(s + ((long)c * kObsH + 2 * Y + dy) * kObsW + x) - c_mean[c]) / c_std[c];
+  }
+  __syncthreads();
+  float4* o = reinterpret_cast<float4*>(out + ((long)b * kS2dH + Y) * (kS2dW * kS2dC));
+  for (int i = threadIdx.x; i < kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,0) of one (X,dy,dx)
+    const int X = i >> 2, dy = (i >> 1) & 1, dx = i & 1;
+    const int x = 2 * X + dx;
+    o[i] = make_float4(tile[0][dy][x], tile[1][dy][x], tile[2][dy][x], 0.f);
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ out,
+                                   int B, int width, long ldo) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)B * width) return;
+  const int b = (int)(i / width), j = (int)(i % width);
+  const long row = idx ? idx[b] : b;
+  out[b * ldo + j] = src[row * width + j];
+}
+
+__global__ void mixup_kernel(const float4* __restrict__ xe, const float4* __restrict__ xp, const float* __restrict__ alpha,
+                             float4* __restrict__ out, long per4) {
+  const int b = blockIdx.y;
+  const float a = alpha[b], na = 1.f - a;
+  const float4* e = xe + b * per4;
+  const float4* q = xp + b * per4;
+  float4* o = out + b * per4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < per4; i += (long)gridDim.x * blockDim.x) {
+    const float4 u = e[i], v = q[i];
+    o[i] = make_float4(a * u.x + na * v.x, a * u.y + na * v.y, a * u.z + na * v.z, a * u.w + na * v.w);
+  }
+}
+
+__device__ __forceinline__ float4 mixed_metrics(const float* m, const float* m2, const float* alpha, int b) {
+  float4 v = *reinterpret_cast<const float4*>(m + 4 * b);
+  if (m2) {
+    const float a = alpha[b], na = 1.f - a;
+    const float4 w = *reinterpret_cast<const float4*>(m2 + 4 * b);
+    v = make_float4(a * v.x + na * w.x, a * v.y + na * w.y, a * v.z + na * w.z, a * v.w + na * w.w);
+  }
+  return v;
+}
+
+__global__ void metrics_features_kernel(const float* __restrict__ m, const float* __restrict__ m2, const float* __restrict__ act,
+                                        const float* __restrict__ act2, const float* __restrict__ alpha,
+                                        const float* __restrict__ emb, float* __restrict__ out, long ldo, int pad, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float4 v = mixed_metrics(m, m2, alpha, b);
+  float* o = out + b * ldo;
+  const float r = sqrtf(v.x * v.x + v.y * v.y);
+  o[0] = 1000.f * v.x;
+  o[1] = 1000.f * v.y;
+  o[2] = 1000.f * r;
+  o[3] = 0.3f * atan2f(v.y, v.x);
+  o[4] = 0.1f * v.z;
+  int c = (int)v.w;  // .long() truncates toward zero (tools/model.py:203-204)
+  c = c < 0 ? 0 : (c > 9 ? 9 : c);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[5 + j] = emb[c * 8 + j];
+  int n = 13;
+  if (act) {
+    float a0 = act[2 * b], a1 = act[2 * b + 1];
+    if (act2) {
+      const float a = alpha[b], na = 1.f - a;
+      a0 = a * a0 + na * act2[2 * b];
+      a1 = a * a1 + na * act2[2 * b + 1];
+    }
+    o[13] = a0;
+    o[14] = a1;
+    n = 15;
+  }
+  for (int j = n; j < pad; ++j) o[j] = 0.f;
+}
+
+__global__ void metrics_features_bwd_kernel(const float* __restrict__ m, const float* __restrict__ m2,
+                                            const float* __restrict__ alpha, const float* __restrict__ dfeat, long ldf,
+                                            float* __restrict__ demb, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 8) return;
+  const int b = i >> 3, j = i & 7;
+  const float4 v = mixed_metrics(m, m2, alpha, b);
+  int c = (int)v.w;
+  c = c < 0 ? 0 : (c > 9 ? 9 : c);
+  atomicAdd(demb + c * 8 + j, dfeat[b * ldf + 5 + j]);
+}
+
+// ---- tiny-N linear layers (head.2: 256->3, trunk.2: 100->1) --------------------------------------------------
+__global__ void small_linear_fwd_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ w,
+                                        const float* __restrict__ bias, float* __restrict__ y, long ldy, int B, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = lane; k < K; k += 32) {
+    const float xv = x[b * ldx + k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < N) acc[j] += xv * __ldg(w + j * K + k);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float s = gc::warp_sum(acc[j]);
+    if (lane == 0 && j < N) y[b * ldy + j] = s + (bias ? bias[j] : 0.f);
+  }
+}
+
+__global__ void small_linear_dx_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ w,
+                                       const float* __restrict__ dy, long lddy, float* __restrict__ dx, long lddx, int B, int N,
+                                       int K, float slope) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)B * K) return;
+  const int b = (int)(i / K), k = (int)(i % K);
+  float s = 0.f;
+  for (int j = 0; j < N; ++j) s += dy[b * lddy + j] * __ldg(w + j * K + k);
+  if (slope >= 0.f) s *= (x[b * ldx + k] > 0.f ? 1.f : slope);
+  dx[b * lddx + k] = s;
+}
+
+// dw[j][k] += sum_b dy[b][j]*x[b][k]; grid (k-chunks, row-chunks); db handled by blockIdx.x == 0
+__global__ void small_linear_dw_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ dy, long lddy,
+                                       float* __restrict__ dw, float* __restrict__ db, int B, int N, int K, int rows_per) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * rows_per, b1 = min(B, b0 + rows_per);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int b = b0; b < b1; ++b) {
+    const float xv = k < K ? x[b * ldx + k] : 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < N) {
+        const float d = dy[b * lddy + j];
+        acc[j] += d * xv;
+        accb[j] += d;
+      }
+  }
+  if (k < K)
+    for (int j = 0; j < N; ++j) atomicAdd(dw + j * K + k, acc[j]);
+  if (db && k == 0)
+    for (int j = 0; j < N; ++j) atomicAdd(db + j, accb[j]);
+}
+
+__global__ void disc_loss_seed_kernel(const float* __restrict__ d, float* __restrict__ dd, double* __restrict__ acc, int B) {
+  __shared__ double red[32 * 4];
+  double part[4] = {0.0, 0.0, 0.0, 0.0};
+  const float invB = 1.f / (float)B;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B; i += gridDim.x * blockDim.x) {
+    const float v = d[i];
+    if (i < 2 * B) {
+      const float t = tanhf(v);
+      const float g = (1.f - t * t) * invB;
+      if (i < B) { dd[i] = -g; part[0] += v; part[2] += t; }
+      else { dd[i] = g; part[1] += v; part[3] += t; }
+    } else {
+      dd[i] = 1.f;
+    }
+  }
+  gc::block_sum<4>(part, red);
+  if (threadIdx.x == 0)
+    for (int j = 0; j < 4; ++j) atomicAdd(acc + j, part[j]);
+}
+
+// one CTA per sample: ||g_raw|| then u = lambda*2*(||g||-1)/(B*||g||) * s_c^2 * g
+__global__ void __launch_bounds__(512) grad_penalty_kernel(const float4* __restrict__ g, float4* __restrict__ u,
+                                                           double* __restrict__ acc, int B, long per4, float lambda_, float s0,
+                                                           float s1, float s2) {
+  __shared__ double red[32];
+  __shared__ float s_coef;
+  const int b = blockIdx.x;
+  const float4* gb = g + b * per4;
+  float4* ub = u + b * per4;
+  float ss = 0.f;
+  double part[1];
+  double tot = 0.0;
+  for (long i = threadIdx.x; i < per4; i += blockDim.x) {
+    const float4 v = gb[i];
+    const float a = v.x * s0, c = v.y * s1, d = v.z * s2;
+    ss += a * a + c * c + d * d;
+    if ((i & 1023) == 1023) { tot += ss; ss = 0.f; }
+  }
+  part[0] = tot + ss;
+  gc::block_sum<1>(part, red);
+  if (threadIdx.x == 0) {
+    const float nrm = (float)sqrt(part[0]);
+    const float diff = nrm - 1.f;
+    atomicAdd(acc, (double)diff * diff);
+    s_coef = nrm > 0.f ? lambda_ * 2.f * diff / ((float)B * nrm) : 0.f;
+  }
+  __syncthreads();
+  const float k0 = s_coef * s0 * s0, k1 = s_coef * s1 * s1, k2 = s_coef * s2 * s2;
+  for (long i = threadIdx.x; i < per4; i += blockDim.x) {
+    const float4 v = gb[i];
+    ub[i] = make_float4(k0 * v.x, k1 * v.y, k2 * v.z, 0.f);
+  }
+}
+
+__global__ void reward_kernel(const float* __restrict__ d, float* __restrict__ r, long n) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float s = 1.f / (1.f + expf(-d[i]));  // torch.sigmoid
+  r[i] = -logf(1.f - s);                      // -(1 - s).log()  (algo/wdgail.py:185-186)
+}
+
+// out[c] += column sums; block = 32 x 8 (columns x row lanes), grid (col chunks, row chunks)
+__global__ void colsum_kernel(const float* __restrict__ x, long ld, long rows, int C, float* __restrict__ out, long rows_per) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long r0 = blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float acc = 0.f;
+  if (c < C)
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) acc += x[r * ld + c];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sm[j][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long M, int N, long ldp,
+                                     const float* __restrict__ bias, const float* __restrict__ mask, long ldm,
+                                     float* __restrict__ out, long ldo, int epi, float slope) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  const long m = i / N;
+  const int n = (int)(i % N);
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[((long)z * M + m) * ldp + n];
+  if (epi == 1 || epi == 2) s += bias[n];
+  if (epi == 1) s = gc::leaky(s, slope);
+  if (epi == 3) s *= (mask[m * ldm + n] > 0.f ? 1.f : slope);
+  out[m * ldo + n] = s;
+}
+
+// ---- parameter layout preparation ----------------------------------------------------------------------------
+// generic conv (layers 2-4): w[n][c][ky][kx]  ->  wf[n][ky][kx][c],  wd[cls][c][a][b'][n]
+__global__ void prep_conv_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd, int Cout, int Cin) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)Cout * Cin * 16;
+  if (i >= total) return;
+  const int kx = (int)(i & 3), ky = (int)((i >> 2) & 3);
+  const int c = (int)((i >> 4) % Cin), n = (int)((i >> 4) / Cin);
+  const float v = w[i];
+  wf[((long)n * 16 + ky * 4 + kx) * Cin + c] = v;
+  if (wd) {
+    const int py = ky & 1, a = ky >> 1, px = kx & 1, bb = kx >> 1;
+    wd[(((long)(py * 2 + px) * Cin + c) * 4 + a * 2 + bb) * Cout + n] = v;
+  }
+}
+// conv1 in space-to-depth form: wf[n][ky2][px][q], q = dy*8+dx*4+c4;  wd[q][a=ky2][b'=px][n]
+__global__ void prep_conv1_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over n(32) x ky2(2) x px(2) x q(16)
+  if (i >= 32 * 64) return;
+  const int q = i & 15, px = (i >> 4) & 1, ky2 = (i >> 5) & 1, n = i >> 6;
+  const int c = q & 3, dx = (q >> 2) & 1, dy = (q >> 3) & 1;
+  const float v = c < 3 ? w[((n * 3 + c) * 4 + (2 * ky2 + dy)) * 4 + (2 * px + dx)] : 0.f;
+  wf[i] = v;
+  if (wd) wd[((q * 2 + ky2) * 2 + px) * 32 + n] = v;
+}
+__global__ void unprep_conv_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw, int Cout, int Cin) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)Cout * Cin * 16;
+  if (i >= total) return;
+  const int kx = (int)(i & 3), ky = (int)((i >> 2) & 3);
+  const int c = (int)((i >> 4) % Cin), n = (int)((i >> 4) / Cin);
+  const long src = ((long)n * 16 + ky * 4 + kx) * Cin + c;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[(long)z * total + src];
+  dw[i] = s;
+}
+__global__ void unprep_conv1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dw[n][c][ky][kx], 32*3*16
+  if (i >= 32 * 48) return;
+  const int kx = i & 3, ky = (i >> 2) & 3, c = (i >> 4) % 3, n = (i >> 4) / 3;
+  const int ky2 = ky >> 1, dy = ky & 1, px = kx >> 1, dx = kx & 1;
+  const int src = ((n * 2 + ky2) * 2 + px) * 16 + dy * 8 + dx * 4 + c;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[z * (32 * 64) + src];
+  dw[i] = s;
+}
+// FC1 column permutation: reference column c*100+p  <->  operand column p*256+c
+__global__ void prep_fc1_kernel(const float* __restrict__ w, float* __restrict__ wg, int out, int tail, long ld) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)out * ld) return;
+  const int o = (int)(i / ld);
+  const long j = i % ld;
+  const long K = kFeat + tail;
+  float v = 0.f;
+  if (j < kFeat) v = w[o * K + (j % kC4) * kPix + (j / kC4)];
+  else if (j < K) v = w[o * K + j];
+  wg[i] = v;
+}
+__global__ void unprep_fc1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw, int out, int tail, long ld) {
+  const long K = kFeat + tail;
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= (long)out * K) return;
+  const int o = (int)(i / K);
+  const long j = i % K;
+  const long src = j < kFeat ? (j % kPix) * kC4 + (j / kPix) : j;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += part[((long)z * out + o) * ld + src];
+  dw[i] = s;
+}
+
+// ---- clip_grad_norm_ + Adam ---------------------------------------------------------------------------------
+__global__ void grad_sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ out) {
+  __shared__ double red[32];
+  float s = 0.f;
+  double tot = 0.0;
+  int cnt = 0;
+  const long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = g4[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    if (++cnt == 64) { tot += s; s = 0.f; cnt = 0; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s += v * v; }
+  double part[1] = {tot + s};
+  gc::block_sum<1>(part, red);
+  if (threadIdx.x == 0) atomicAdd(out, part[0]);
+}
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float coef, float lr_c, float b1, float b2, float eps,
+                                      float inv_sqrt_bc2) {
+  g *= coef;
+  m = b1 * m + (1.f - b1) * g;
+  v = b2 * v + (1.f - b2) * g * g;
+  const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+  p -= lr_c * (m / denom);
+}
+
+__global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
+                                 const double* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps,
+                                 float bc1, float bc2) {
+  float coef = 1.f;
+  if (max_norm >= 0.f) {
+    const float total = (float)sqrt(*sumsq);
+    coef = fminf(max_norm / (total + 1e-6f), 1.f);
+  }
+  const float lr_c = lr / bc1, isb = 1.f / sqrtf(bc2);
+  const long n4 = n >> 2;
+  float4 *p4 = reinterpret_cast<float4*>(p), *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
+  float4* g4 = reinterpret_cast<float4*>(g);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 P = p4[i], G = g4[i], M = m4[i], V = v4[i];
+    adam1(P.x, G.x, M.x, V.x, coef, lr_c, b1, b2, eps, isb);
+    adam1(P.y, G.y, M.y, V.y, coef, lr_c, b1, b2, eps, isb);
+    adam1(P.z, G.z, M.z, V.z, coef, lr_c, b1, b2, eps, isb);
+    adam1(P.w, G.w, M.w, V.w, coef, lr_c, b1, b2, eps, isb);
+    p4[i] = P; m4[i] = M; v4[i] = V;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long i = (n4 << 2) + threadIdx.x;
+    adam1(p[i], g[i], m[i], v[i], coef, lr_c, b1, b2, eps, isb);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B, void* stream) {
+  GC_REQUIRE(src && out && B > 0, "gc_gather_obs_s2d: bad arguments");
+  GC_REQUIRE(B <= 65535, "gc_gather_obs_s2d: B=%d exceeds grid.y", B);
+  gather_obs_s2d_kernel<<<dim3(kS2dH, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
+  return gc::launch_status("gather_obs_s2d_kernel");
+}
+
+int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream) {
+  GC_REQUIRE(src && out && B > 0 && width > 0 && ldo >= width, "gc_gather_rows: bad arguments");
+  const long n = (long)B * width;
+  gather_rows_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, idx, out, B, width, ldo);
+  return gc::launch_status("gather_rows_kernel");
+}
+
+int gc_mixup(const float* xe, const float* xp, const float* alpha, float* out, int B, long per_sample, void* stream) {
+  GC_REQUIRE(xe && xp && alpha && out && B > 0 && per_sample > 0 && per_sample % 4 == 0 && B <= 65535, "gc_mixup: bad arguments");
+  const long per4 = per_sample / 4;
+  const int gx = (int)std::min<long>((per4 + 255) / 256, 64);
+  mixup_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>((const float4*)xe, (const float4*)xp, alpha, (float4*)out, per4);
+  return gc::launch_status("mixup_kernel");
+}
+
+int gc_metrics_features(const float* metrics, const float* metrics2, const float* action, const float* action2,
+                        const float* alpha, const float* emb, float* out, long ldo, int pad, int B, void* stream) {
+  GC_REQUIRE(metrics && emb && out && B > 0, "gc_metrics_features: bad arguments");
+  GC_REQUIRE((metrics2 == nullptr) == (alpha == nullptr), "gc_metrics_features: metrics2 and alpha go together");
+  GC_REQUIRE(pad >= (action ? 15 : 13) && ldo >= pad, "gc_metrics_features: pad/ldo too small");
+  metrics_features_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(metrics, metrics2, action, action2, alpha, emb, out,
+                                                                             ldo, pad, B);
+  return gc::launch_status("metrics_features_kernel");
+}
+
+int gc_metrics_features_bwd(const float* metrics, const float* metrics2, const float* alpha, const float* d_feat, long ldf,
+                            float* d_emb, int B, void* stream) {
+  GC_REQUIRE(metrics && d_feat && d_emb && B > 0, "gc_metrics_features_bwd: bad arguments");
+  metrics_features_bwd_kernel<<<(B * 8 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(metrics, metrics2, alpha, d_feat, ldf, d_emb, B);
+  return gc::launch_status("metrics_features_bwd_kernel");
+}
+
+int gc_small_linear_fwd(const float* x, long ldx, const float* w, const float* bias, float* y, long ldy, int B, int N, int K,
+                        void* stream) {
+  GC_REQUIRE(x && w && y && B > 0 && N >= 1 && N <= 4 && K > 0, "gc_small_linear_fwd: bad arguments (N must be 1..4)");
+  const long threads = (long)B * 32;
+  small_linear_fwd_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y, ldy, B, N, K);
+  return gc::launch_status("small_linear_fwd_kernel");
+}
+
+int gc_small_linear_bwd(const float* x, long ldx, const float* w, const float* dy, long lddy, float* dx, long lddx, float* dw,
+                        float* db, int B, int B_params, int N, int K, float slope, void* stream) {
+  GC_REQUIRE(x && w && dy && B > 0 && N >= 1 && N <= 4 && K > 0 && B_params <= B, "gc_small_linear_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    const long n = (long)B * K;
+    small_linear_dx_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(x, ldx, w, dy, lddy, dx, lddx, B, N, K, slope);
+    if (int e = gc::launch_status("small_linear_dx_kernel")) return e;
+  }
+  if (dw && B_params > 0) {
+    const int rows_per = 256;
+    dim3 grid((K + 127) / 128, (B_params + rows_per - 1) / rows_per);
+    small_linear_dw_kernel<<<grid, 128, 0, st>>>(x, ldx, dy, lddy, dw, db, B_params, N, K, rows_per);
+    if (int e = gc::launch_status("small_linear_dw_kernel")) return e;
+  }
+  return 0;
+}
+
+int gc_disc_loss_seed(const float* d, float* dd, double* acc, int B, void* stream) {
+  GC_REQUIRE(d && dd && acc && B > 0, "gc_disc_loss_seed: bad arguments");
+  disc_loss_seed_kernel<<<grid_for(3L * B, 256, 2), 256, 0, (cudaStream_t)stream>>>(d, dd, acc, B);
+  return gc::launch_status("disc_loss_seed_kernel");
+}
+
+int gc_grad_penalty(const float* g, float* u, double* acc, int B, long per_sample, float lambda_, float s0, float s1, float s2,
+                    void* stream) {
+  GC_REQUIRE(g && u && acc && B > 0 && per_sample % 4 == 0, "gc_grad_penalty: bad arguments");
+  grad_penalty_kernel<<<B, 512, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)u, acc, B, per_sample / 4, lambda_, s0, s1, s2);
+  return gc::launch_status("grad_penalty_kernel");
+}
+
+int gc_reward_epilogue(const float* d, float* reward, long n, void* stream) {
+  GC_REQUIRE(d && reward && n > 0, "gc_reward_epilogue: bad arguments");
+  reward_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, reward, n);
+  return gc::launch_status("reward_kernel");
+}
+
+int gc_colsum(const float* x, long ld, long rows, int C, float* out, void* stream) {
+  GC_REQUIRE(x && out && rows > 0 && C > 0 && ld >= C, "gc_colsum: bad arguments");
+  const int cx = (C + 31) / 32;
+  long chunks = std::max<long>(1, std::min<long>((rows + 63) / 64, (4L * gc::kNumSMs) / cx + 1));
+  const long rows_per = (rows + chunks - 1) / chunks;
+  chunks = (rows + rows_per - 1) / rows_per;
+  colsum_kernel<<<dim3(cx, (unsigned)chunks), dim3(32, 8), 0, (cudaStream_t)stream>>>(x, ld, rows, C, out, rows_per);
+  return gc::launch_status("colsum_kernel");
+}
+
+int gc_splitk_reduce(const float* part, int splits, long M, int N, long ldp, const float* bias, const float* mask_src, long ldm,
+                     float* out, long ldo, int epilogue, float slope, void* stream) {
+  GC_REQUIRE(part && out && splits >= 1 && M > 0 && N > 0, "gc_splitk_reduce: bad arguments");
+  if (epilogue == 1 || epilogue == 2) GC_REQUIRE(bias, "gc_splitk_reduce: bias epilogue without bias");
+  if (epilogue == 3) GC_REQUIRE(mask_src, "gc_splitk_reduce: mask epilogue without mask source");
+  const long n = M * N;
+  splitk_reduce_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, splits, M, N, ldp, bias, mask_src, ldm, out, ldo,
+                                                                               epilogue, slope);
+  return gc::launch_status("splitk_reduce_kernel");
+}
+
+int gc_prep_conv_weight(const float* w, float* w_fprop, float* w_dgrad, int Cout, int Cin, int layer1, void* stream) {
+  GC_REQUIRE(w && w_fprop, "gc_prep_conv_weight: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layer1) {
+    GC_REQUIRE(Cout == 32 && Cin == 3, "gc_prep_conv_weight: layer1 expects 32x3x4x4");
+    prep_conv1_kernel<<<8, 256, 0, st>>>(w, w_fprop, w_dgrad);
+  } else {
+    const long n = (long)Cout * Cin * 16;
+    prep_conv_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w, w_fprop, w_dgrad, Cout, Cin);
+  }
+  return gc::launch_status("prep_conv_kernel");
+}
+
+int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, int Cout, int Cin, int layer1, void* stream) {
+  GC_REQUIRE(part && dw && splits >= 1, "gc_unprep_conv_wgrad: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (layer1) {
+    GC_REQUIRE(Cout == 32 && Cin == 3, "gc_unprep_conv_wgrad: layer1 expects 32x3x4x4");
+    unprep_conv1_kernel<<<6, 256, 0, st>>>(part, splits, dw);
+  } else {
+    const long n = (long)Cout * Cin * 16;
+    unprep_conv_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, splits, dw, Cout, Cin);
+  }
+  return gc::launch_status("unprep_conv_kernel");
+}
+
+int gc_prep_fc1_weight(const float* w, float* w_gemm, int out, int tail, long ld, void* stream) {
+  GC_REQUIRE(w && w_gemm && out > 0 && tail >= 0 && ld >= kFeat + tail, "gc_prep_fc1_weight: bad arguments");
+  const long n = (long)out * ld;
+  prep_fc1_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, w_gemm, out, tail, ld);
+  return gc::launch_status("prep_fc1_kernel");
+}
+
+int gc_unprep_fc1_wgrad(const float* part, int splits, float* dw, int out, int tail, long ld, void* stream) {
+  GC_REQUIRE(part && dw && out > 0 && splits >= 1 && ld >= kFeat + tail, "gc_unprep_fc1_wgrad: bad arguments");
+  const long n = (long)out * (kFeat + tail);
+  unprep_fc1_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, splits, dw, out, tail, ld);
+  return gc::launch_status("unprep_fc1_kernel");
+}
+
+int gc_grad_sumsq(const float* grad, long n, double* sumsq, void* stream) {
+  GC_REQUIRE(grad && sumsq && n > 0, "gc_grad_sumsq: bad arguments");
+  GC_REQUIRE(((uintptr_t)grad & 15) == 0, "gc_grad_sumsq: grad must be 16-byte aligned");
+  grad_sumsq_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(grad, n, sumsq);
+  return gc::launch_status("grad_sumsq_kernel");
+}
+
+int gc_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long n, const double* sumsq, float max_norm,
+                 float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2, void* stream) {
+  GC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "gc_clip_adam: bad arguments");
+  GC_REQUIRE(max_norm < 0.f || sumsq, "gc_clip_adam: clipping needs sumsq");
+  GC_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
+             "gc_clip_adam: buffers must be 16-byte aligned");
+  clip_adam_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm,
+                                                                               lr, beta1, beta2, eps, bias_corr1, bias_corr2);
+  return gc::launch_status("clip_adam_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,514 @@
+// Host side of the tcgen05 GEMM engine: tensor-map construction, tile-shape selection and the C-ABI entry points
+// gc_conv_fprop / gc_conv_dgrad / gc_conv_wgrad / gc_linear_fwd / gc_linear_dgrad / gc_linear_wgrad.
+// Reference op sites: tools/model.py:131-164 (conv stack), :89-128 (FC body/head), algo/wdgail.py:26-32 (critic trunk),
+// algo/wdgail.py:56-98 (gradient-penalty chains reuse dgrad / fprop-with-mask / wgrad).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
+#include "gc_umma_kernel.cuh"
+#include "../../include/gail_carla_b200.h"
+
+namespace {
+using namespace gcu;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+struct MapSpec {
+  const void* ptr;
+  uint64_t dim[5];
+  uint64_t stride[4];  // bytes, dims 1..4
+  uint32_t box[5];
+  int tf32;     // operand maps round fp32 -> tf32 (RN) inside TMA; output / mask maps stay fp32
+  int swizzle;  // SWIZZLE_128B or none
+};
+
+std::unordered_map<std::string, CUtensorMap>& map_cache() {
+  static std::unordered_map<std::string, CUtensorMap> c;
+  return c;
+}
+std::mutex& map_mutex() {
+  static std::mutex m;
+  return m;
+}
+
+int make_map(const MapSpec& s, CUtensorMap* out) {
+  std::string key((const char*)&s, sizeof(MapSpec));
+  {
+    std::lock_guard<std::mutex> g(map_mutex());
+    auto it = map_cache().find(key);
+    if (it != map_cache().end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return gc::fail(-3, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) { dims[i] = s.dim[i]; box[i] = s.box[i]; }
+  for (int i = 0; i < 4; ++i) strides[i] = s.stride[i];
+  CUresult r = fn(out, s.tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.ptr, dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  s.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return gc::fail((int)r,
+                    "cuTensorMapEncodeTiled failed (%d): ptr=%p dim=[%llu,%llu,%llu,%llu,%llu] stride=[%llu,%llu,%llu,%llu] "
+                    "box=[%u,%u,%u,%u,%u]",
+                    (int)r, s.ptr, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                    (unsigned long long)dims[3], (unsigned long long)dims[4], (unsigned long long)strides[0],
+                    (unsigned long long)strides[1], (unsigned long long)strides[2], (unsigned long long)strides[3], box[0],
+                    box[1], box[2], box[3], box[4]);
+  std::lock_guard<std::mutex> g(map_mutex());
+  if (map_cache().size() > 4096) map_cache().clear();
+  map_cache()[key] = *out;
+  return 0;
+}
+
+// MapSpec builder: dims given innermost first; missing dims are padded with extent 1.
+MapSpec spec(const void* ptr, int rank, const uint64_t* dim, const uint64_t* stride_elems, const uint32_t* box, int tf32,
+             int swizzle) {
+  MapSpec s;
+  memset(&s, 0, sizeof(s));
+  s.ptr = ptr;
+  uint64_t last = 16;
+  for (int i = 0; i < 5; ++i) {
+    s.dim[i] = i < rank ? dim[i] : 1;
+    s.box[i] = i < rank ? box[i] : 1;
+    if (i >= 1) {
+      if (i < rank) s.stride[i - 1] = stride_elems[i] * 4;
+      else s.stride[i - 1] = last;
+      last = s.stride[i - 1] * std::max<uint64_t>(1, s.dim[i]);
+    } else {
+      last = std::max<uint64_t>(16, s.dim[0] * 4);
+    }
+  }
+  s.tf32 = tf32;
+  s.swizzle = swizzle;
+  return s;
+}
+
+int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+struct Plan {
+  GemmParams p;
+  dim3 grid;
+  bool a_mn, b_mn;
+  Plan() { memset(&p, 0, sizeof(p)); p.e0 = p.e1 = p.f0 = p.g0 = p.g1 = 1; a_mn = b_mn = false; }
+};
+
+constexpr int kSmemBudget = 225 * 1024;
+
+int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
+  GemmParams& p = pl.p;
+  GC_REQUIRE(p.bn % 16 == 0 && p.bn >= 16 && p.bn <= 256, "%s: tile N %d not a multiple of 16 in [16,256]", what, p.bn);
+  GC_REQUIRE(p.bk % 8 == 0 && p.bk >= 8, "%s: bk %d not a multiple of 8", what, p.bk);
+  if (!pl.a_mn || !pl.b_mn) GC_REQUIRE(p.bk == 32, "%s: K-major operands need bk == 32 (got %d)", what, p.bk);
+  p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
+  const int bpan = (p.bn + 31) / 32;
+  p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
+  p.b_bytes = (p.b_bytes + 1023) & ~1023;
+  p.nbuf = p.epilogue == EPI_MASK ? 4 : 2;
+  p.tmem_cols = pow2_cols(bpan * 32);
+  p.d_row_bytes = p.bn >= 32 ? 128 : p.bn * 4;
+  const int stage = p.a_bytes + p.b_bytes;
+  const int fixed = p.nbuf * 16384 + 2048;
+  int stages = (kSmemBudget - fixed) / stage;
+  stages = std::min(stages, 8);
+  stages = std::min(stages, std::max(2, p.k_iters));
+  GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B)", what, stage);
+  // short K loops: prefer two co-resident CTAs per SM (one's epilogue overlaps the other's mainloop)
+  if (p.k_iters <= 96) {
+    const int half = (kSmemBudget / 2 - 1024 - fixed) / stage;
+    if (half >= 2) stages = std::min(stages, std::min(half, 4));
+  }
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage + fixed;
+  auto launch = [&](auto kern) -> int {
+    static thread_local const void* configured[3] = {nullptr, nullptr, nullptr};
+    (void)configured;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    kern<<<pl.grid, 192, smem, st>>>(p);
+    return gc::launch_status(what);
+  };
+  if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false>);
+  if (!pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<false, true>);
+  if (pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<true, true>);
+  return gc::fail(-2, "%s: unsupported operand majors", what);
+}
+
+// ---- pixel-box selection -------------------------------------------------------------------
+struct PixBox { int ox, oy, b; };
+
+// Tile of output pixels (ox fastest, then oy, then samples) with at most `max_rows` rows whose row count is a
+// multiple of `mult`; maximise useful rows / issued rows.
+PixBox choose_box(int OW, int OH, int B, int max_rows, int mult, double small_penalty) {
+  PixBox best{1, 1, 1};
+  double best_score = -1.0;
+  for (int bx = 1; bx <= std::min(OW, max_rows); ++bx) {
+    for (int by = 1; by <= OH && bx * by <= max_rows; ++by) {
+      const int bb_max = (bx == OW && by == OH) ? std::min(B, max_rows / (bx * by)) : 1;
+      for (int bb = 1; bb <= bb_max; ++bb) {
+        const int rows = bx * by * bb;
+        if (rows % mult) continue;
+        const long tiles = (long)((OW + bx - 1) / bx) * ((OH + by - 1) / by) * ((B + bb - 1) / bb);
+        const double issued = (double)tiles * (small_penalty > 0 ? rows : max_rows);
+        double score = (double)OW * OH * B / issued;
+        if (small_penalty > 0) score -= small_penalty / rows;  // fewer, fatter k-iterations amortise barriers
+        if (score > best_score + 1e-9) { best_score = score; best = PixBox{bx, by, bb}; }
+      }
+    }
+  }
+  return best;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int check_geom(const gc_conv_geom* g, const char* what) {
+  GC_REQUIRE(g != nullptr, "%s: null geometry", what);
+  GC_REQUIRE(g->B > 0 && g->Cin > 0 && g->Cout > 0 && g->KH > 0 && g->KW > 0 && g->S > 0, "%s: bad geometry", what);
+  GC_REQUIRE((g->KW * g->Cin) % 32 == 0, "%s: KW*Cin=%d must be a multiple of 32", what, g->KW * g->Cin);
+  GC_REQUIRE(g->Cout % 16 == 0, "%s: Cout=%d must be a multiple of 16", what, g->Cout);
+  GC_REQUIRE((g->OH - 1) * g->S + g->KH <= g->H && (g->OW - 1) * g->S + g->KW <= g->W, "%s: output does not fit input", what);
+  GC_REQUIRE(g->Wp >= g->W && g->Hp >= g->H && g->OWp >= g->OW && g->OHp >= g->OH, "%s: pitches smaller than extents", what);
+  GC_REQUIRE(g->in_batch_stride >= (long)g->Hp * g->Wp * g->Cin && g->out_batch_stride >= (long)g->OHp * g->OWp * g->Cout,
+             "%s: batch strides too small", what);
+  GC_REQUIRE(g->in_batch_stride % 4 == 0 && g->out_batch_stride % 4 == 0, "%s: batch strides must be multiples of 4 floats", what);
+  return 0;
+}
+
+// A-operand window map over x[B][Hp][Wp][Cin]: dims (kx*c, ox, ky, oy, b) - overlapping strides
+MapSpec window_spec(const gc_conv_geom* g, const float* x, const PixBox& bx) {
+  const uint64_t dim[5] = {(uint64_t)g->KW * g->Cin, (uint64_t)g->OW, (uint64_t)g->KH, (uint64_t)g->OH, (uint64_t)g->B};
+  const uint64_t str[5] = {1, (uint64_t)g->S * g->Cin, (uint64_t)g->Wp * g->Cin, (uint64_t)g->S * g->Wp * g->Cin,
+                           (uint64_t)g->in_batch_stride};
+  const uint32_t box[5] = {32, (uint32_t)bx.ox, 1, (uint32_t)bx.oy, (uint32_t)bx.b};
+  return spec(x, 5, dim, str, box, 1, 1);
+}
+
+// map over y[B][OHp][OWp][Cout]: dims (n, ox, oy, b)
+MapSpec out_spec(const gc_conv_geom* g, const float* y, const PixBox& bx, int inner, int tf32, int swz) {
+  const uint64_t dim[4] = {(uint64_t)g->Cout, (uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->B};
+  const uint64_t str[4] = {1, (uint64_t)g->Cout, (uint64_t)g->OWp * g->Cout, (uint64_t)g->out_batch_stride};
+  const uint32_t box[4] = {(uint32_t)inner, (uint32_t)bx.ox, (uint32_t)bx.oy, (uint32_t)bx.b};
+  return spec(y, 4, dim, str, box, tf32, swz);
+}
+
+}  // namespace
+
+// ============================================ C ABI ============================================
+extern "C" {
+
+// y[b,oy,ox,n] = epi( sum_{ky,kx,c} x[b, S*oy+ky, S*ox+kx, c] * w[n][ky][kx][c] )
+int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const float* bias, const float* mask_src,
+                  float* y, int epilogue, float slope, void* stream) {
+  if (int e = check_geom(g, "gc_conv_fprop")) return e;
+  GC_REQUIRE(x && w && y, "gc_conv_fprop: null pointer");
+  GC_REQUIRE(epilogue >= 0 && epilogue <= 3, "gc_conv_fprop: bad epilogue %d", epilogue);
+  if (epilogue == EPI_BIAS_LRELU || epilogue == EPI_BIAS) GC_REQUIRE(bias, "gc_conv_fprop: bias epilogue without bias");
+  if (epilogue == EPI_MASK) GC_REQUIRE(mask_src, "gc_conv_fprop: mask epilogue without mask source");
+  Plan pl;
+  GemmParams& p = pl.p;
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, 128, 1, 0.0);
+  const int K = g->KH * g->KW * g->Cin;
+  p.bn = std::min(256, g->Cout);
+  p.bk = 32;
+  p.e0 = cdiv(g->OW, bx.ox);
+  p.e1 = cdiv(g->OH, bx.oy);
+  const int e2 = cdiv(g->B, bx.b);
+  p.f0 = cdiv(g->Cout, p.bn);
+  p.g0 = g->KW * g->Cin / 32;
+  p.g1 = g->KH;
+  p.k_iters = p.g0 * p.g1;
+  // A: window map
+  if (int e = make_map(window_spec(g, x, bx), &p.mapA)) return e;
+  p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[2][K1] = 1; p.a.mul[3][M1] = bx.oy; p.a.mul[4][M2] = bx.b;
+  p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
+  // B: weights [Cout][K]
+  {
+    const uint64_t dim[2] = {(uint64_t)K, (uint64_t)g->Cout}, str[2] = {1, (uint64_t)K};
+    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+  }
+  p.b.mul[0][K0] = 32; p.b.mul[0][K1] = 32 * p.g0; p.b.mul[1][N0] = p.bn;
+  p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  // D (+ mask source with the same geometry)
+  const int inner = std::min(32, p.bn);
+  if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD)) return e;
+  if (epilogue == EPI_MASK) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX)) return e; }
+  else p.mapX = p.mapD;
+  p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
+  p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
+  p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
+  pl.grid = dim3(p.e0 * p.e1 * e2, p.f0, 1);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_fprop");
+}
+
+// dx[b, S*j+py, S*i+px, c] = mask * sum_{a,b',n} dy[b, j-a, i-b', n] * wd[cls][c][a][b'][n],  cls = py*S+px,
+// taps a < KH/S, b' < KW/S.  One launch per parity class.  mask = LeakyReLU'(sign of mask_src at the output position).
+int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, float* dx, float slope,
+                  void* stream) {
+  if (int e = check_geom(g, "gc_conv_dgrad")) return e;
+  GC_REQUIRE(dy && wd && dx, "gc_conv_dgrad: null pointer");
+  GC_REQUIRE(g->KH % g->S == 0 && g->KW % g->S == 0, "gc_conv_dgrad: taps must be a multiple of the stride");
+  GC_REQUIRE(g->Cout % 32 == 0 && g->Cin % 16 == 0 && g->Cin <= 256, "gc_conv_dgrad: Cout%%32, Cin%%16, Cin<=256 required");
+  const int TA = g->KH / g->S, TB = g->KW / g->S;
+  const int Kd = TA * TB * g->Cout;
+  for (int py = 0; py < g->S; ++py) {
+    for (int px = 0; px < g->S; ++px) {
+      const int NJ = cdiv(g->H - py, g->S), NI = cdiv(g->W - px, g->S);
+      Plan pl;
+      GemmParams& p = pl.p;
+      const PixBox bx = choose_box(NI, NJ, g->B, 128, 1, 0.0);
+      p.bn = g->Cin;
+      p.bk = 32;
+      p.e0 = cdiv(NI, bx.ox);
+      p.e1 = cdiv(NJ, bx.oy);
+      const int e2 = cdiv(g->B, bx.b);
+      p.f0 = 1;
+      p.g0 = g->Cout / 32;
+      p.g1 = TB;
+      p.k_iters = p.g0 * TB * TA;
+      // A: dy[B][OHp][OWp][Cout] read at (j - a, i - b'); out-of-range taps are zero-filled by TMA
+      if (int e = make_map(out_spec(g, dy, bx, 32, 1, 1), &p.mapA)) return e;
+      p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[1][K1] = -1; p.a.mul[2][M1] = bx.oy; p.a.mul[2][K2] = -1;
+      p.a.mul[3][M2] = bx.b;
+      p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
+      // B: wd[cls][Cin][Kd], k = (a*TB + b')*Cout + n
+      {
+        const uint64_t dim[3] = {(uint64_t)Kd, (uint64_t)g->Cin, (uint64_t)(g->S * g->S)};
+        const uint64_t str[3] = {1, (uint64_t)Kd, (uint64_t)Kd * g->Cin};
+        const uint32_t box[3] = {32, (uint32_t)p.bn, 1};
+        if (int e = make_map(spec(wd, 3, dim, str, box, 1, 1), &p.mapB)) return e;
+      }
+      p.b.mul[0][K0] = 32; p.b.mul[0][K1] = g->Cout; p.b.mul[0][K2] = TB * g->Cout; p.b.off[2] = py * g->S + px;
+      p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+      // D / mask: dx[B][Hp][Wp][Cin] restricted to the parity class
+      const int inner = std::min(32, p.bn);
+      const long base = ((long)py * g->Wp + px) * g->Cin;
+      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)NI, (uint64_t)NJ, (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)g->S * g->Cin, (uint64_t)g->S * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
+      const uint32_t box[4] = {(uint32_t)inner, (uint32_t)bx.ox, (uint32_t)bx.oy, (uint32_t)bx.b};
+      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, p.bn >= 32), &p.mapD)) return e;
+      if (mask_src) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, p.bn >= 32), &p.mapX)) return e; }
+      else p.mapX = p.mapD;
+      p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
+      p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
+      p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = g->Cin;
+      pl.grid = dim3(p.e0 * p.e1 * e2, 1, 1);
+      if (int e = finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_dgrad")) return e;
+    }
+  }
+  return 0;
+}
+
+int gc_conv_wgrad_splits(const gc_conv_geom* g) {
+  if (check_geom(g, "gc_conv_wgrad_splits")) return -1;
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, 64, 8, 4.0);
+  const int btiles = cdiv(g->B, bx.b);
+  const int bn = std::min(256, g->KW * g->Cin);
+  const int tiles = cdiv(g->Cout, 128) * (g->KW * g->Cin / bn) * g->KH;
+  int z = std::max(1, std::min(btiles, (2 * gc::kNumSMs) / std::max(1, tiles)));
+  return z;
+}
+
+// dw_partial[z][n][ky][kx*c] = sum over the z-th slice of samples of dy[pix][n] * x[window(pix)][ky][kx*c]
+int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float* dw_partial, int splits, void* stream) {
+  if (int e = check_geom(g, "gc_conv_wgrad")) return e;
+  GC_REQUIRE(dy && x && dw_partial, "gc_conv_wgrad: null pointer");
+  GC_REQUIRE(g->Cout % 32 == 0, "gc_conv_wgrad: Cout %% 32 required");
+  GC_REQUIRE(splits >= 1, "gc_conv_wgrad: splits=%d", splits);
+  Plan pl;
+  GemmParams& p = pl.p;
+  pl.a_mn = pl.b_mn = true;
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, 64, 8, 4.0);
+  const int KC = g->KW * g->Cin;
+  p.bn = std::min(256, KC);
+  GC_REQUIRE(KC % p.bn == 0, "gc_conv_wgrad: KW*Cin=%d not a multiple of tile N %d", KC, p.bn);
+  p.bk = bx.ox * bx.oy * bx.b;
+  p.e0 = cdiv(g->Cout, 128);
+  p.e1 = 1;
+  p.f0 = KC / p.bn;
+  p.g0 = cdiv(g->OW, bx.ox);
+  p.g1 = cdiv(g->OH, bx.oy);
+  const int btiles = cdiv(g->B, bx.b);
+  const int g2 = cdiv(btiles, splits);
+  p.k_iters = p.g0 * p.g1 * g2;
+  // A: dy MN-major, panels of 32 output channels
+  if (int e = make_map(out_spec(g, dy, bx, 32, 1, 1), &p.mapA)) return e;
+  p.a.mul[0][M0] = 128; p.a.mul[1][K0] = bx.ox; p.a.mul[2][K1] = bx.oy; p.a.mul[3][K2] = bx.b; p.a.mul[3][Z] = g2 * bx.b;
+  p.a.panel[0] = 32;
+  p.a_panels = std::min(4, g->Cout / 32); p.a_panel_bytes = p.bk * 128;
+  // B: x windows MN-major, panels of 32 (kx,c) columns
+  if (int e = make_map(window_spec(g, x, bx), &p.mapB)) return e;
+  p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = bx.ox; p.b.mul[2][N1] = 1; p.b.mul[3][K1] = bx.oy; p.b.mul[4][K2] = bx.b;
+  p.b.mul[4][Z] = g2 * bx.b; p.b.panel[0] = 32;
+  p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
+  // D: partial[z][Cout][KH][KC]
+  {
+    const uint64_t dim[4] = {(uint64_t)KC, (uint64_t)g->KH, (uint64_t)g->Cout, (uint64_t)splits};
+    const uint64_t str[4] = {1, (uint64_t)KC, (uint64_t)g->KH * KC, (uint64_t)g->Cout * g->KH * KC};
+    const int rows = std::min(128, g->Cout);
+    const uint32_t box[4] = {32, 1, (uint32_t)rows, 1};
+    if (int e = make_map(spec(dw_partial, 4, dim, str, box, 0, 1), &p.mapD)) return e;
+    p.d_box_bytes = rows * 128;
+  }
+  p.mapX = p.mapD;
+  p.d.mul[0][N0] = p.bn; p.d.mul[1][N1] = 1; p.d.mul[2][M0] = 128; p.d.mul[3][Z] = 1; p.d.panel[0] = 32;
+  p.epilogue = EPI_STORE; p.n_total = KC;
+  pl.grid = dim3(p.e0, p.f0 * g->KH, splits);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_wgrad");
+}
+
+// y[z][m][n] = epi( sum_{k in split z} x[m][k] * w[n][k] ); x row pitch ldx, w row pitch ldw (floats, multiples of 4)
+int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const float* bias, float* y, long ldy, int M, int N,
+                  int K, int epilogue, float slope, int splits, void* stream) {
+  GC_REQUIRE(x && w && y && M > 0 && N > 0 && K > 0, "gc_linear_fwd: bad arguments");
+  GC_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "gc_linear_fwd: row pitches must be multiples of 4 floats");
+  GC_REQUIRE(epilogue == EPI_STORE || epilogue == EPI_BIAS_LRELU || epilogue == EPI_BIAS, "gc_linear_fwd: bad epilogue");
+  GC_REQUIRE(splits >= 1 && (splits == 1 || epilogue == EPI_STORE), "gc_linear_fwd: split-K needs the plain-store epilogue");
+  if (epilogue != EPI_STORE) GC_REQUIRE(bias, "gc_linear_fwd: bias epilogue without bias");
+  Plan pl;
+  GemmParams& p = pl.p;
+  p.bn = std::min(256, ((N + 15) / 16) * 16);
+  p.bk = 32;
+  p.e0 = cdiv(M, 128);
+  p.f0 = cdiv(N, p.bn);
+  const int kit_total = cdiv(K, 32);
+  p.k_iters = cdiv(kit_total, splits);
+  p.kz_stride = p.k_iters;
+  p.g0 = 1 << 30;
+  {
+    const uint64_t dim[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {1, (uint64_t)ldx};
+    const uint32_t box[2] = {32, 128};
+    if (int e = make_map(spec(x, 2, dim, str, box, 1, 1), &p.mapA)) return e;
+  }
+  p.a.mul[0][K0] = 32; p.a.mul[1][M0] = 128; p.a_panels = 1; p.a_panel_bytes = 16384;
+  {
+    const uint64_t dim[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {1, (uint64_t)ldw};
+    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+  }
+  p.b.mul[0][K0] = 32; p.b.mul[1][N0] = p.bn; p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  {
+    const int inner = std::min(32, p.bn);
+    const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)ldy, (uint64_t)ldy * M};
+    const uint32_t box[3] = {(uint32_t)inner, 128, 1};
+    if (int e = make_map(spec(y, 3, dim, str, box, 0, p.bn >= 32), &p.mapD)) return e;
+    p.d_box_bytes = inner * 4 * 128;
+  }
+  p.mapX = p.mapD;
+  p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.mul[2][Z] = 1; p.d.panel[0] = 32;
+  p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = N;
+  pl.grid = dim3(p.e0, p.f0, splits);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_linear_fwd");
+}
+
+// dx[m][n] = mask * sum_k dy[m][k] * w[k][n]   (w is the forward weight [out=K][in=N], read MN-major - no transpose)
+int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, long ldm, float* dx,
+                    long lddx, int M, int N, int K, float slope, void* stream) {
+  GC_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, "gc_linear_dgrad: bad arguments");
+  GC_REQUIRE(lddy % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 && ldm % 4 == 0, "gc_linear_dgrad: pitches must be multiples of 4");
+  Plan pl;
+  GemmParams& p = pl.p;
+  pl.b_mn = true;
+  p.bn = std::min(256, ((N + 31) / 32) * 32);
+  p.bk = 32;
+  p.e0 = cdiv(M, 128);
+  p.f0 = cdiv(N, p.bn);
+  p.k_iters = cdiv(K, 32);
+  p.g0 = 1 << 30;
+  {
+    const uint64_t dim[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {1, (uint64_t)lddy};
+    const uint32_t box[2] = {32, 128};
+    if (int e = make_map(spec(dy, 2, dim, str, box, 1, 1), &p.mapA)) return e;
+  }
+  p.a.mul[0][K0] = 32; p.a.mul[1][M0] = 128; p.a_panels = 1; p.a_panel_bytes = 16384;
+  {
+    const uint64_t dim[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)ldw};
+    const uint32_t box[2] = {32, 32};
+    if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+  }
+  p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = 32; p.b.panel[0] = 32; p.b_panels = p.bn / 32; p.b_panel_bytes = 32 * 128;
+  {
+    const uint64_t dim[2] = {(uint64_t)N, (uint64_t)M}, str[2] = {1, (uint64_t)lddx};
+    const uint32_t box[2] = {32, 128};
+    if (int e = make_map(spec(dx, 2, dim, str, box, 0, 1), &p.mapD)) return e;
+    if (mask_src) {
+      const uint64_t strm[2] = {1, (uint64_t)ldm};
+      if (int e = make_map(spec(mask_src, 2, dim, strm, box, 0, 1), &p.mapX)) return e;
+    } else p.mapX = p.mapD;
+    p.d_box_bytes = 128 * 128;
+  }
+  p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.panel[0] = 32;
+  p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = N;
+  pl.grid = dim3(p.e0, p.f0, 1);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_linear_dgrad");
+}
+
+// dw[z][m][n] = sum_{rows in split z} dy[row][m] * x[row][n]   (both operands MN-major - no transposes)
+int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float* dw, long lddw, int M, int N, int K, int splits,
+                    void* stream) {
+  GC_REQUIRE(dy && x && dw && M > 0 && N > 0 && K > 0 && splits >= 1, "gc_linear_wgrad: bad arguments");
+  GC_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && lddw % 4 == 0, "gc_linear_wgrad: pitches must be multiples of 4");
+  Plan pl;
+  GemmParams& p = pl.p;
+  pl.a_mn = pl.b_mn = true;
+  p.bn = std::min(256, ((N + 31) / 32) * 32);
+  p.bk = 32;
+  p.e0 = cdiv(M, 128);
+  p.f0 = cdiv(N, p.bn);
+  const int kit_total = cdiv(K, p.bk);
+  p.k_iters = cdiv(kit_total, splits);
+  p.kz_stride = p.k_iters;
+  p.g0 = 1 << 30;
+  {
+    const uint64_t dim[2] = {(uint64_t)M, (uint64_t)K}, str[2] = {1, (uint64_t)lddy};
+    const uint32_t box[2] = {32, (uint32_t)p.bk};
+    if (int e = make_map(spec(dy, 2, dim, str, box, 1, 1), &p.mapA)) return e;
+  }
+  p.a.mul[0][M0] = 128; p.a.mul[1][K0] = p.bk; p.a.panel[0] = 32;
+  p.a_panels = std::min(4, cdiv(M, 32)); p.a_panel_bytes = p.bk * 128;
+  {
+    const uint64_t dim[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)ldx};
+    const uint32_t box[2] = {32, (uint32_t)p.bk};
+    if (int e = make_map(spec(x, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+  }
+  p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = p.bk; p.b.panel[0] = 32; p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
+  {
+    const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)lddw, (uint64_t)lddw * M};
+    const uint32_t box[3] = {32, 128, 1};
+    if (int e = make_map(spec(dw, 3, dim, str, box, 0, 1), &p.mapD)) return e;
+    p.d_box_bytes = 128 * 128;
+  }
+  p.mapX = p.mapD;
+  p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.mul[2][Z] = 1; p.d.panel[0] = 32;
+  p.epilogue = EPI_STORE; p.n_total = N;
+  pl.grid = dim3(p.e0, p.f0, splits);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_linear_wgrad");
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// tcgen05 / TMEM / TMA "affine-tile" TF32 GEMM engine for sm_100a.
+//
+// One kernel serves every dense contraction of the policy / discriminator trunks
+// (tools/model.py:89-164, algo/wdgail.py:26-32,56-98): conv fprop / dgrad / wgrad as implicit GEMMs and the
+// fully-connected fwd / dgrad / wgrad.  D[M,N] = sum_k A[M,k] * B[N,k] with
+//   * operands fetched by 5-D TMA boxes whose coordinates are affine functions of the tile index, the
+//     k-iteration index and blockIdx.z (so im2col windows, parity-class dgrad taps, split-K and batched
+//     pixel boxes are all just coefficient tables filled in on the host - no im2col buffer, no transposes),
+//   * either operand K-major (rows of 32 tf32 = 128 B, SWIZZLE_128B) or MN-major (panels of 32 tf32 along
+//     M/N x bk rows along K), chosen per operand through the UMMA instruction descriptor,
+//   * tcgen05.mma.kind::tf32 (M=128, N=16..256, K=8) issued by one thread, fp32 accumulators in TMEM,
+//   * a 4-warp epilogue (tcgen05.ld -> bias / LeakyReLU / LeakyReLU'-mask -> swizzled smem -> TMA store);
+//     TMA clips partial tiles on store and zero-fills them on load, so the kernel has no bounds logic.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace gcu {
+
+constexpr int kSrc = 9;  // coordinate sources: m0 m1 m2 | n0 n1 | k0 k1 k2 | z
+enum Src { M0 = 0, M1, M2, N0, N1, K0, K1, K2, Z };
+
+struct TmaAddr {
+  int off[5];
+  int mul[5][kSrc];
+  int panel[5];  // added once per panel (successive TMA boxes of one operand / successive 32-column output panels)
+};
+
+enum Epilogue { EPI_STORE = 0, EPI_BIAS_LRELU = 1, EPI_BIAS = 2, EPI_MASK = 3 };
+
+struct alignas(64) GemmParams {
+  CUtensorMap mapA, mapB, mapD, mapX;
+  TmaAddr a, b, d;
+  int e0, e1;          // m-tile index -> (m0, m1, m2) extents
+  int f0;              // n-tile index -> (n0, n1)
+  int g0, g1;          // k-iteration -> (k0, k1, k2)
+  int k_iters;         // k-iterations per CTA
+  int kz_stride;       // k-iteration offset per blockIdx.z (flat split-K), else 0
+  int bk;              // K elements per k-iteration (32 for K-major operands; multiple of 8)
+  int bn;              // tile N (multiple of 16, <= 256)
+  int a_panels, b_panels, a_panel_bytes, b_panel_bytes;
+  int a_bytes, b_bytes;  // per-stage region sizes
+  int stages;
+  int tmem_cols;
+  int epilogue;
+  int n_total;         // valid output columns (bias guard)
+  int d_row_bytes;     // 128 (swizzled staging) or bn*4 when bn < 32 (unswizzled)
+  int d_box_bytes;     // bytes of one output / mask TMA box (rows may be < 128)
+  int nbuf;            // staging buffers: 2, or 4 with EPI_MASK
+  float slope;
+  const float* bias;
+};
+
+}  // namespace gcu

@@ -1,0 +1,313 @@
+// The tcgen05 / TMEM / TMA kernel behind every dense contraction (see gc_umma.cuh for the design).
+#pragma once
+#include "gc_common.cuh"
+#include "gc_umma.cuh"
+
+namespace gcu {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a barrier that never completes (a descriptor / byte-count bug) traps after ~4 s instead of
+// hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 8000000000LL) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, const int (&c)[5]) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, const int (&c)[5]) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"((uint64_t)map), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc], int lo, int hi, int (&c)[5]) {
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    int v = 0;
+    for (int s = lo; s < hi; ++s) v += t.mul[d][s] * src[s];
+    c[d] += v;
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+// warps 0-3: epilogue (TMEM lanes 32w..32w+31) | warp 4: TMA producer + TMEM owner | warp 5: MMA issuer
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = p.a_bytes + p.b_bytes;
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;  // 2 x 16 KB, 1024-aligned
+  uint64_t* bars = (uint64_t*)(staging + (size_t)p.nbuf * 16384);
+  // bars: full[stages], empty[stages], tmem_full, aux[4]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
+  const uint32_t tmem_full = empty0 + 8 * p.stages, aux0 = tmem_full + 8;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(aux0 + 8 * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_async_smem();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile-constant coordinate sources
+  int src[kSrc];
+  {
+    const int mt = blockIdx.x;
+    src[M0] = mt % p.e0;
+    const int t = mt / p.e0;
+    src[M1] = t % p.e1;
+    src[M2] = t / p.e1;
+    src[N0] = blockIdx.y % p.f0;
+    src[N1] = blockIdx.y / p.f0;
+    src[K0] = src[K1] = src[K2] = 0;
+    src[Z] = blockIdx.z;
+  }
+
+  if (warp == 4) {
+    if (lane == 0) {
+      int baseA[5], baseB[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) { baseA[d] = p.a.off[d]; baseB[d] = p.b.off[d]; }
+      coords(p.a, src, 0, 5, baseA);
+      coords(p.b, src, 0, 5, baseB);
+      coords(p.a, src, Z, Z + 1, baseA);
+      coords(p.b, src, Z, Z + 1, baseB);
+      const uint32_t tx = p.a_panels * p.a_panel_bytes + p.b_panels * p.b_panel_bytes;
+      for (int it = 0; it < p.k_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(full0 + 8 * s, tx);
+        const int kit = it + blockIdx.z * p.kz_stride;
+        src[K0] = kit % p.g0;
+        const int t = kit / p.g0;
+        src[K1] = t % p.g1;
+        src[K2] = t / p.g1;
+        int ca[5], cb[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) { ca[d] = baseA[d]; cb[d] = baseB[d]; }
+        coords(p.a, src, K0, K2 + 1, ca);
+        coords(p.b, src, K0, K2 + 1, cb);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+        for (int q = 0; q < p.a_panels; ++q) {
+          tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, ca);
+#pragma unroll
+          for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
+        }
+        for (int q = 0; q < p.b_panels; ++q) {
+          tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+      const int ksteps = p.bk >> 3;
+      const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
+      const uint32_t b_lbo = B_MN ? (uint32_t)p.b_panel_bytes : 0u;
+      for (int it = 0; it < p.k_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, 1024);
+          const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (it | ks) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue: thread t owns accumulator row 32*warp + lane ----------------
+    // Output goes out in 32-column panels through `nbuf` 16 KB staging buffers.  With EPI_MASK the panel's
+    // LeakyReLU' source tile (same box geometry as the output) is TMA-loaded into the staging buffer two
+    // panels ahead, multiplied in place and stored from the same buffer.
+    const int row = warp * 32 + lane;
+    const int n_panels = (p.bn + 31) >> 5;
+    const bool swz = p.d_row_bytes == 128;
+    const bool masked = p.epilogue == EPI_MASK;
+    const int nbuf = p.nbuf;
+    int cd[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) cd[d] = p.d.off[d];
+    coords(p.d, src, 0, 5, cd);
+    coords(p.d, src, Z, Z + 1, cd);
+    if (masked && threadIdx.x == 0) {  // prefetch mask tiles of panels 0 and 1 while the mainloop runs
+      for (int q = 0; q < 2 && q < n_panels; ++q) {
+        int cx[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cx[d] = cd[d] + q * p.d.panel[d];
+        mbar_expect_tx(aux0 + 8 * q, (uint32_t)p.d_box_bytes);
+        tma_load_5d(smem_u32(staging + q * 16384), &p.mapX, aux0 + 8 * q, cx);
+      }
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int q = 0; q < n_panels; ++q) {
+      uint8_t* buf = staging + (q % nbuf) * 16384;
+      if (threadIdx.x == 0 && q >= 2) {
+        tma_wait_read<1>();  // store of panel q-2 has drained its staging buffer
+      }
+      if (masked && threadIdx.x == 0 && q + 2 < n_panels) {
+        // buffer (q+2)%4 was last read by the store of panel q-2 (drained above); fetch mask tile q+2 into it
+        const int j = (q + 2) % nbuf;
+        int cx[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) cx[d] = cd[d] + 2 * p.d.panel[d];
+        mbar_expect_tx(aux0 + 8 * j, (uint32_t)p.d_box_bytes);
+        tma_load_5d(smem_u32(staging + j * 16384), &p.mapX, aux0 + 8 * j, cx);
+      }
+      epi_bar_sync();
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
+      const int col0 = blockIdx.y * p.bn + q * 32;
+      if (p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float b = (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
+          const float x = v[j] + b;
+          v[j] = (p.epilogue == EPI_BIAS_LRELU) ? gc::leaky(x, p.slope) : x;
+        }
+      }
+      const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
+      const int nchunk = p.d_row_bytes >> 4;
+      if (masked) {
+        mbar_wait(aux0 + 8 * (q % nbuf), (q / nbuf) & 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nchunk) {
+            uint32_t o = rbase + j * 16;
+            if (swz) o ^= ((o >> 7) & 7) << 4;
+            const float4 m = *reinterpret_cast<const float4*>(buf + o);
+            v[4 * j + 0] *= m.x > 0.f ? 1.f : p.slope;
+            v[4 * j + 1] *= m.y > 0.f ? 1.f : p.slope;
+            v[4 * j + 2] *= m.z > 0.f ? 1.f : p.slope;
+            v[4 * j + 3] *= m.w > 0.f ? 1.f : p.slope;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < nchunk) {
+          uint32_t o = rbase + j * 16;
+          if (swz) o ^= ((o >> 7) & 7) << 4;
+          *reinterpret_cast<float4*>(buf + o) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      fence_async_smem();
+      epi_bar_sync();
+      if (threadIdx.x == 0) {
+        tma_store_5d(&p.mapD, smem_u32(buf), cd);
+        tma_commit();
+      }
+#pragma unroll
+      for (int d = 0; d < 5; ++d) cd[d] += p.d.panel[d];
+    }
+    if (threadIdx.x == 0) tma_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+  }
+}
+
+}  // namespace gcu
