@@ -37,7 +37,7 @@ struct MapSpec {
   uint64_t stride[4];  // bytes, dims 1..4
   uint32_t box[5];
   int tf32;     // operand maps round fp32 -> tf32 (RN) inside TMA; output / mask maps stay fp32
-  int swizzle;  // SWIZZLE_128B or none
+  int swizzle;  // 0 none | 1 SWIZZLE_128B (K-major operands, output staging) | 2 SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
 };
 
 std::unordered_map<std::string, CUtensorMap>& map_cache() {
@@ -67,7 +67,9 @@ int make_map(const MapSpec& s, CUtensorMap* out) {
   for (int i = 0; i < 4; ++i) strides[i] = s.stride[i];
   CUresult r = fn(out, s.tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.ptr, dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  s.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  s.swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                 : (s.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return gc::fail((int)r,
@@ -170,7 +172,7 @@ PixBox choose_box(int OW, int OH, int B, int max_rows, int mult, double small_pe
   double best_score = -1.0;
   for (int bx = 1; bx <= std::min(OW, max_rows); ++bx) {
     for (int by = 1; by <= OH && bx * by <= max_rows; ++by) {
-      const int bb_max = (bx == OW && by == OH) ? std::min(B, max_rows / (bx * by)) : 1;
+      const int bb_max = (bx == OW) ? std::min(B, max_rows / (bx * by)) : 1;
       for (int bb = 1; bb <= bb_max; ++bb) {
         const int rows = bx * by * bb;
         if (rows % mult) continue;
@@ -201,12 +203,12 @@ int check_geom(const gc_conv_geom* g, const char* what) {
 }
 
 // A-operand window map over x[B][Hp][Wp][Cin]: dims (kx*c, ox, ky, oy, b) - overlapping strides
-MapSpec window_spec(const gc_conv_geom* g, const float* x, const PixBox& bx) {
+MapSpec window_spec(const gc_conv_geom* g, const float* x, const PixBox& bx, int swz = 1) {
   const uint64_t dim[5] = {(uint64_t)g->KW * g->Cin, (uint64_t)g->OW, (uint64_t)g->KH, (uint64_t)g->OH, (uint64_t)g->B};
   const uint64_t str[5] = {1, (uint64_t)g->S * g->Cin, (uint64_t)g->Wp * g->Cin, (uint64_t)g->S * g->Wp * g->Cin,
                            (uint64_t)g->in_batch_stride};
   const uint32_t box[5] = {32, (uint32_t)bx.ox, 1, (uint32_t)bx.oy, (uint32_t)bx.b};
-  return spec(x, 5, dim, str, box, 1, 1);
+  return spec(x, 5, dim, str, box, 1, swz);
 }
 
 // map over y[B][OHp][OWp][Cout]: dims (n, ox, oy, b)
@@ -325,9 +327,17 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
   return 0;
 }
 
+// K rows (pixels) per k-iteration for wgrad: a multiple of 8 that leaves room for >= 3 pipeline stages
+static int wgrad_max_rows(int bn) {
+  const int per_row = 128 * (4 + bn / 32);
+  int r = ((kSmemBudget - 2 * 16384 - 2048) / 3) / per_row;
+  r = (r / 8) * 8;
+  return std::max(8, std::min(64, r));
+}
+
 int gc_conv_wgrad_splits(const gc_conv_geom* g) {
   if (check_geom(g, "gc_conv_wgrad_splits")) return -1;
-  const PixBox bx = choose_box(g->OW, g->OH, g->B, 64, 8, 4.0);
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(std::min(256, g->KW * g->Cin)), 8, 4.0);
   const int btiles = cdiv(g->B, bx.b);
   const int bn = std::min(256, g->KW * g->Cin);
   const int tiles = cdiv(g->Cout, 128) * (g->KW * g->Cin / bn) * g->KH;
@@ -344,9 +354,9 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
   Plan pl;
   GemmParams& p = pl.p;
   pl.a_mn = pl.b_mn = true;
-  const PixBox bx = choose_box(g->OW, g->OH, g->B, 64, 8, 4.0);
   const int KC = g->KW * g->Cin;
   p.bn = std::min(256, KC);
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(p.bn), 8, 4.0);
   GC_REQUIRE(KC % p.bn == 0, "gc_conv_wgrad: KW*Cin=%d not a multiple of tile N %d", KC, p.bn);
   p.bk = bx.ox * bx.oy * bx.b;
   p.e0 = cdiv(g->Cout, 128);
@@ -358,12 +368,12 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
   const int g2 = cdiv(btiles, splits);
   p.k_iters = p.g0 * p.g1 * g2;
   // A: dy MN-major, panels of 32 output channels
-  if (int e = make_map(out_spec(g, dy, bx, 32, 1, 1), &p.mapA)) return e;
+  if (int e = make_map(out_spec(g, dy, bx, 32, 1, 2), &p.mapA)) return e;
   p.a.mul[0][M0] = 128; p.a.mul[1][K0] = bx.ox; p.a.mul[2][K1] = bx.oy; p.a.mul[3][K2] = bx.b; p.a.mul[3][Z] = g2 * bx.b;
   p.a.panel[0] = 32;
   p.a_panels = std::min(4, g->Cout / 32); p.a_panel_bytes = p.bk * 128;
   // B: x windows MN-major, panels of 32 (kx,c) columns
-  if (int e = make_map(window_spec(g, x, bx), &p.mapB)) return e;
+  if (int e = make_map(window_spec(g, x, bx, 2), &p.mapB)) return e;
   p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = bx.ox; p.b.mul[2][N1] = 1; p.b.mul[3][K1] = bx.oy; p.b.mul[4][K2] = bx.b;
   p.b.mul[4][Z] = g2 * bx.b; p.b.panel[0] = 32;
   p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
@@ -450,7 +460,7 @@ int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const 
   {
     const uint64_t dim[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)ldw};
     const uint32_t box[2] = {32, 32};
-    if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+    if (int e = make_map(spec(w, 2, dim, str, box, 1, 2), &p.mapB)) return e;
   }
   p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = 32; p.b.panel[0] = 32; p.b_panels = p.bn / 32; p.b_panel_bytes = 32 * 128;
   {
@@ -488,14 +498,14 @@ int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float*
   {
     const uint64_t dim[2] = {(uint64_t)M, (uint64_t)K}, str[2] = {1, (uint64_t)lddy};
     const uint32_t box[2] = {32, (uint32_t)p.bk};
-    if (int e = make_map(spec(dy, 2, dim, str, box, 1, 1), &p.mapA)) return e;
+    if (int e = make_map(spec(dy, 2, dim, str, box, 1, 2), &p.mapA)) return e;
   }
   p.a.mul[0][M0] = 128; p.a.mul[1][K0] = p.bk; p.a.panel[0] = 32;
   p.a_panels = std::min(4, cdiv(M, 32)); p.a_panel_bytes = p.bk * 128;
   {
     const uint64_t dim[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)ldx};
     const uint32_t box[2] = {32, (uint32_t)p.bk};
-    if (int e = make_map(spec(x, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+    if (int e = make_map(spec(x, 2, dim, str, box, 1, 2), &p.mapB)) return e;
   }
   p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = p.bk; p.b.panel[0] = 32; p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
   {

@@ -80,14 +80,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
-// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type.
+// K-major operands: SWIZZLE_128B (2), 8-row groups 1024 B apart.  MN-major tf32 operands only exist as
+// SWIZZLE_128B_BASE32B (1): 128 B rows of 32 elements along M/N, 4-row K atoms 512 B apart (SBO), 32-element panels LBO apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -205,8 +207,8 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
         for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, 1024);
-          const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, 1024);
+          const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+          const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
           umma_tf32(tmem_base, ad, bd, idesc, (it | ks) ? 1u : 0u);
         }
         umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire

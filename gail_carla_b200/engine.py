@@ -1,0 +1,245 @@
+"""Host-side orchestration of the trunks: parameter flattening, operand-layout preparation, workspaces, and the
+forward / hand-derived backward passes of the policy (tools/model.py:56-128) and of the WDGAIL critic including the
+gradient-penalty second-order pass (algo/wdgail.py:40-98).  All arithmetic happens in the C-ABI kernels (``_abi``);
+this module only sequences launches and owns device buffers (allocated through torch, i.e. plumbing).
+
+Layouts: images are space-to-depth NHWC ``[B,96,96,16]`` (normalised, pad channel 0), conv
+activations NHWC (conv1 output with row/column pitch 96), conv4 output lands directly in the feature matrix
+``F[B, LDF]`` (LDF = 25600 + 32) whose last 32 columns hold the 13 metric features (+2 action columns for the critic).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _abi as A
+from ._abi import ConvGeom, LDF, S2D_PER_SAMPLE, EPI_BIAS, EPI_BIAS_LRELU, EPI_MASK, EPI_STORE
+
+SLOPE = 0.2                      # nn.LeakyReLU(0.2) everywhere (tools/model.py:138-144,95-99,112)
+FEAT = 25600
+CONV_CH = (3, 32, 64, 128, 256)
+INV_STD = (1.0 / 0.229, 1.0 / 0.224, 1.0 / 0.225)   # tools/model.py:155
+ALIGN = 64                       # every parameter starts on a 256-byte boundary inside the flat buffers
+
+
+def conv_geom(layer: int, B: int) -> ConvGeom:
+    """Implicit-GEMM geometry of conv `layer` (1-based) of ProcessObsFeatures (tools/model.py:137-143)."""
+    if layer == 1:   # k4,s2 on [192,192,3] == k2,s1 on the space-to-depth image [96,96,16]
+        return ConvGeom(B, 96, 96, 96, 96, 16, 2, 2, 1, 95, 95, 96, 96, 32, 96 * 96 * 16, 96 * 96 * 32)
+    if layer == 2:
+        return ConvGeom(B, 95, 95, 96, 96, 32, 4, 4, 2, 46, 46, 46, 46, 64, 96 * 96 * 32, 46 * 46 * 64)
+    if layer == 3:
+        return ConvGeom(B, 46, 46, 46, 46, 64, 4, 4, 2, 22, 22, 22, 22, 128, 46 * 46 * 64, 22 * 22 * 128)
+    if layer == 4:
+        return ConvGeom(B, 22, 22, 22, 22, 128, 4, 4, 2, 10, 10, 10, 10, 256, 22 * 22 * 128, LDF)
+    raise ValueError(layer)
+
+
+def conv_geom4_compact(B: int) -> ConvGeom:
+    """conv4 with a compact [B,10,10,256] output side (used for gradients w.r.t. the conv features)."""
+    return ConvGeom(B, 22, 22, 22, 22, 128, 4, 4, 2, 10, 10, 10, 10, 256, 22 * 22 * 128, FEAT)
+
+
+ACT_ELEMS = (S2D_PER_SAMPLE, 96 * 96 * 32, 46 * 46 * 64, 22 * 22 * 128)   # per-sample floats of X0, A1, A2, A3
+
+
+class FlatParams:
+    """All parameters of a module as views into one flat fp32 buffer (same for grads and Adam moments), so that
+    clip_grad_norm_ + Adam (algo/ppo.py:115-119) is two launches and the NCCL gradient all-reduce is one bucket."""
+
+    def __init__(self, module: nn.Module):
+        self.module = module
+        self.names: List[str] = []
+        self.offsets: Dict[str, int] = {}
+        self.flat = self.grad = None
+        self.rebuild()
+
+    def rebuild(self) -> None:
+        params = list(self.module.named_parameters())
+        dev = params[0][1].device
+        off = 0
+        self.names, self.offsets = [], {}
+        for n, p in params:
+            self.names.append(n)
+            self.offsets[n] = off
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        self.numel = off
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        for n, p in params:
+            o = self.offsets[n]
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1).float())
+            p.data = flat[o:o + p.numel()].view(p.shape)
+            p.grad = grad[o:o + p.numel()].view(p.shape)
+        self.flat, self.grad = flat, grad
+
+    def ok(self) -> bool:
+        """True while every parameter is still a view of the flat buffer (``.to()`` / ``.cpu()`` break that)."""
+        base = self.flat.data_ptr()
+        for n, p in self.module.named_parameters():
+            if p.data_ptr() != base + 4 * self.offsets[n] or p.grad is None or p.device != self.flat.device:
+                return False
+        return True
+
+    def ensure(self) -> bool:
+        if not self.ok():
+            self.rebuild()
+            return True
+        return False
+
+    def g(self, name: str) -> torch.Tensor:
+        return self.module.get_parameter(name).grad
+
+    def p(self, name: str) -> torch.Tensor:
+        return self.module.get_parameter(name).data
+
+
+class Workspace:
+    """Device buffers for one trunk at a given row capacity.  Gradient buffers are created on first backward."""
+
+    def __init__(self, device, rows: int, with_input_grad: bool):
+        self.device, self.rows = device, rows
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        self.X0 = z(rows, S2D_PER_SAMPLE)
+        self.A = [self.X0, z(rows, ACT_ELEMS[1]), z(rows, ACT_ELEMS[2]), z(rows, ACT_ELEMS[3])]
+        self.F = z(rows, LDF)
+        self.dA: Optional[List[torch.Tensor]] = None
+        self.with_input_grad = with_input_grad
+        self.part: Dict[str, torch.Tensor] = {}
+        self.small: Dict[str, torch.Tensor] = {}
+
+    def grads(self):
+        if self.dA is None:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
+            self.dA = [z(self.rows, S2D_PER_SAMPLE) if self.with_input_grad else None,
+                       z(self.rows, ACT_ELEMS[1]), z(self.rows, ACT_ELEMS[2]), z(self.rows, ACT_ELEMS[3]),
+                       z(self.rows, FEAT)]
+            self.dFt = z(self.rows, 32)
+        return self.dA
+
+    def buf(self, key: str, *shape) -> torch.Tensor:
+        t = self.small.get(key)
+        n = math.prod(shape)
+        if t is None or t.numel() < n:
+            t = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.small[key] = t
+        return t[:n].view(*shape)
+
+    def partial(self, key: str, numel: int) -> torch.Tensor:
+        t = self.part.get(key)
+        if t is None or t.numel() < numel:
+            t = torch.empty(numel, dtype=torch.float32, device=self.device)
+            self.part[key] = t
+        return t
+
+
+def _splits_for(m_tiles: int, n_tiles: int, k_iters: int, cap: int = 8) -> int:
+    tiles = max(1, m_tiles * n_tiles)
+    s = max(1, min(cap, (2 * 148) // tiles))
+    return max(1, min(s, k_iters // 8 if k_iters >= 16 else 1))
+
+
+class ConvStack:
+    """The four Conv2d(k4,s2)+LeakyReLU layers + flatten of ProcessObsFeatures (tools/model.py:131-164)."""
+
+    def __init__(self, flat: FlatParams, prefix: str, need_input_grad: bool):
+        self.flat, self.prefix, self.need_input_grad = flat, prefix, need_input_grad
+        self.wf: List[torch.Tensor] = []
+        self.wd: List[Optional[torch.Tensor]] = []
+        self._dev = None
+
+    def wname(self, i: int) -> str:
+        return f"{self.prefix}main.{2 * (i - 1)}.weight"
+
+    def bname(self, i: int) -> str:
+        return f"{self.prefix}main.{2 * (i - 1)}.bias"
+
+    def prepare(self) -> None:
+        """(Re)build the GEMM operand copies of the conv weights after the parameters changed."""
+        dev = self.flat.flat.device
+        if self._dev != dev:
+            self.wf, self.wd = [], []
+            for i in range(1, 5):
+                n = 2048 if i == 1 else CONV_CH[i] * CONV_CH[i - 1] * 16
+                self.wf.append(torch.zeros(n, dtype=torch.float32, device=dev))
+                need_wd = i > 1 or self.need_input_grad
+                self.wd.append(torch.zeros(n, dtype=torch.float32, device=dev) if need_wd else None)
+            self._dev = dev
+        for i in range(1, 5):
+            A.prep_conv_weight(self.flat.p(self.wname(i)), self.wf[i - 1], self.wd[i - 1], CONV_CH[i], CONV_CH[i - 1], i == 1)
+
+    def forward(self, ws: Workspace, B: int, row0: int = 0) -> None:
+        """X0[row0:row0+B] -> A1, A2, A3 -> F[:, :25600] (bias + LeakyReLU fused in the GEMM epilogue)."""
+        for i in range(1, 5):
+            x = ws.A[i - 1][row0:]
+            y = ws.F[row0:] if i == 4 else ws.A[i][row0:]
+            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], self.flat.p(self.bname(i)), y, EPI_BIAS_LRELU, SLOPE)
+
+    def forward_masked(self, ws: Workspace, B: int, row0: int) -> None:
+        """Second-order chain of the gradient penalty: v_k = LeakyReLU'(a_k) * conv_k(v_{k-1}) written in place of
+        a_k (no bias) for rows [row0,row0+B).  ws.X0 rows must already hold u = d gp / d g."""
+        for i in range(1, 5):
+            x = ws.A[i - 1][row0:]
+            y = ws.F[row0:] if i == 4 else ws.A[i][row0:]
+            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], None, y, EPI_MASK, SLOPE, mask_src=y)
+
+    def backward_data(self, ws: Workspace, B: int, row0: int = 0) -> None:
+        """delta_4 (= ws.dA[4], already multiplied by LeakyReLU'(a_4)) -> delta_3, delta_2, delta_1 for rows
+        [row0,row0+B); each dgrad epilogue applies LeakyReLU' of the layer it lands on."""
+        dA = ws.grads()
+        for i in (4, 3, 2):
+            g = conv_geom4_compact(B) if i == 4 else conv_geom(i, B)
+            A.conv_dgrad(g, dA[i][row0:], self.wd[i - 1], dA[i - 1][row0:], ws.A[i - 1][row0:], SLOPE)
+
+    def input_grad(self, ws: Workspace, B: int, row0: int) -> None:
+        """dX0 = conv1^T(delta_1) for rows [row0,row0+B): the dD/dx of algo/wdgail.py:85-91 (normalised-input space)."""
+        dA = ws.grads()
+        A.conv_dgrad(conv_geom(1, B), dA[1][row0:], self.wd[0], dA[0][row0:], None, SLOPE)
+
+    def backward_params(self, ws: Workspace, B: int, B_bias: int) -> None:
+        """Weight gradients from (delta_k, a_{k-1}) over rows [0,B); bias gradients over rows [0,B_bias)."""
+        dA = ws.grads()
+        for i in range(1, 5):
+            g = conv_geom4_compact(B) if i == 4 else conv_geom(i, B)
+            splits = A.conv_wgrad_splits(g)
+            n = 2048 if i == 1 else CONV_CH[i] * CONV_CH[i - 1] * 16
+            part = ws.partial(f"cw{i}", splits * n)
+            A.conv_wgrad(g, dA[i], ws.A[i - 1], part, splits)
+            A.unprep_conv_wgrad(part, splits, self.flat.g(self.wname(i)), CONV_CH[i], CONV_CH[i - 1], i == 1)
+            if B_bias > 0:
+                rows = B_bias * (96 * 96, 46 * 46, 22 * 22, 100)[i - 1]
+                A.colsum(dA[i], CONV_CH[i], rows, CONV_CH[i], self.flat.g(self.bname(i)))
+
+
+def linear_fwd(ws: Workspace, key: str, x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue) -> None:
+    """nn.Linear forward with split-K when the tile grid would leave most SMs idle."""
+    bn = min(256, (N + 15) // 16 * 16)
+    splits = _splits_for((M + 127) // 128, (N + bn - 1) // bn, (K + 31) // 32)
+    if splits == 1:
+        A.linear_fwd(x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue, SLOPE, 1)
+        return
+    ldp = (N + 3) // 4 * 4
+    part = ws.partial(key, splits * M * ldp)
+    A.linear_fwd(x, ldx, w, ldw, None, part, ldp, M, N, K, EPI_STORE, SLOPE, splits)
+    A.splitk_reduce(part, splits, M, N, ldp, bias, None, 0, y, ldy, epilogue, SLOPE)
+
+
+def linear_wgrad(ws: Workspace, key: str, dy, lddy, x, ldx, dw, lddw, M, N, K) -> None:
+    bn = min(256, (N + 31) // 32 * 32)
+    splits = _splits_for((M + 127) // 128, (N + bn - 1) // bn, (K + 31) // 32)
+    if splits == 1:
+        A.linear_wgrad(dy, lddy, x, ldx, dw, lddw, M, N, K, 1)
+        return
+    part = ws.partial(key, splits * M * lddw)
+    A.linear_wgrad(dy, lddy, x, ldx, part, lddw, M, N, K, splits)
+    A.splitk_reduce(part, splits, M, N, lddw, None, None, 0, dw, lddw, EPI_STORE, SLOPE)
+
+
+class MLPSpec:
+    """One hidden nn.Linear + LeakyReLU layer handled by the tensor-core GEMM (weight read in place)."""
+
+    def __init__(self, name: str, fin: int, fout: int):
+        self.name, self.fin, self.fout = name, fin, fout

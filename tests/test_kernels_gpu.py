@@ -48,7 +48,7 @@ def test_gae_matches_reference_golden(name):
     close(out, torch.from_numpy(z["adv_norm"]), 1e-4, 1e-5, "adv_norm")
     stats2 = torch.zeros(4, dtype=torch.float64, device=DEV)
     A.adv_stats(ret, v, stats2, T * N)
-    close(stats2[:3], stats[:3], 1e-9, 1e-9, "stats")
+    close(stats2[:3], stats[:3], 1e-6, 1e-6, "stats")
 
 
 @pytest.mark.parametrize("T,N", [(1, 1), (7, 3), (128, 1), (513, 40), (1024, 64), (512, 256), (37, 1000)])
