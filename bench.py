@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Benchmark of the gail-carla learning hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c4|c2|c5|tiny]
+
+A *step* is one full PPO+WDGAIL update on a collected rollout (tools/learn.py:137-223,269 minus diagnostics):
+bootstrap value -> Discriminator.update x gail_epoch -> predict_reward over all T*N -> compute_returns (GAE) ->
+PPO.update -> after_update.  Metric: env-steps/s = T*N / step time, whole job over all ranks (strong scaling: the
+rollout and the minibatch are split across ranks by environment, gradients are all-reduced with NCCL).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace as NS
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HP = dict(lr=1e-4, eps=1e-8, betas=(0.9, 0.99), clip_param=0.1, value_loss_coef=0.5, max_grad_norm=0.5,
+          gail_lr=2.5e-4, gail_eps=1e-8, gail_betas=(0.9, 0.99), gail_max_grad_norm=0.5, gamma=0.99, gae_lambda=0.95,
+          logstd=[-1.4, -3.2])   # params_variable.json:29-55
+
+CONFIGS = {
+    # BASELINE.json configs[3]: the configuration the env-steps/s metric is quoted on
+    "c4": dict(T=1024, N=64, B_ppo=4096, B_gail=4096, ppo_epoch=1, gail_epoch=1,
+               workload="configs[3]: full PPO+WDGAIL update epoch, 64 envs x 1024 steps, B=4096"),
+    "c5": dict(T=512, N=256, B_ppo=4096, B_gail=4096, ppo_epoch=10, gail_epoch=1,
+               workload="configs[4]: 256 envs x 512 steps, 10 PPO epochs x 32 minibatches"),
+    "tiny": dict(T=64, N=8, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1, workload="tiny: 8 envs x 64 steps, B=128"),
+    # the bounded sample the CPU arm runs: configs[0] verbatim
+    "c1": dict(T=128, N=1, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1,
+               workload="configs[0]: 1 env x 128 steps, B=128"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops_sustained"], bf16_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, bf16=1400.0, bf16_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU torch path for the same update, through the oracle restatement (oracle/ref_path.py, pinned
+    against the unmodified reference - the reference tree itself does not exist on the GPU box), all host threads,
+    on a bounded sample of the workload: configs[0] (1 env x 128 steps, B=128), one full update per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gail_carla_b200 import synthetic
+    from oracle import ref_path as O
+    torch.set_num_threads(os.cpu_count())
+    c = CONFIGS["c1"]
+    T, N = c["T"], c["N"]
+
+    def one_update():
+        torch.manual_seed(1)
+        pol, disc = O.init_policy_params(), O.init_disc_params()
+        padam = O.AdamState(pol, HP["lr"], HP["eps"], HP["betas"]); dadam = O.AdamState(disc, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"])
+        ro = NS(obs=torch.zeros(T + 1, N, 3, 192, 192), metrics=torch.zeros(T + 1, N, 4), actions=torch.zeros(T, N, 2),
+                action_log_probs=torch.zeros(T, N, 1), value_preds=torch.zeros(T + 1, N, 1), returns=torch.zeros(T + 1, N, 1),
+                masks=torch.ones(T + 1, N, 1), gail_rewards=torch.zeros(T, N, 1), rewards=torch.zeros(T, N, 1),
+                num_steps=T, num_processes=N)
+        synthetic.fill_rollout(ro, seed=11)
+        loader = synthetic.SyntheticExpertLoader(T * N // c["B_gail"], c["B_gail"], seed=21)
+        d = {k: getattr(ro, k) for k in ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks",
+                                        "gail_rewards", "rewards")}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            d["value_preds"][-1] = O.policy_base(pol, d["obs"][-1], d["metrics"][-1], True, HP["logstd"])[0]
+        for _ in range(c["gail_epoch"]):
+            O.disc_update(disc, dadam, loader, d, HP["gail_max_grad_norm"])
+        for step in range(T):
+            d["gail_rewards"][step] = O.predict_reward(disc, d["obs"][step], d["metrics"][step], d["actions"][step])
+        d["returns"] = O.gae_returns(d["gail_rewards"], d["value_preds"], d["masks"], HP["gamma"], HP["gae_lambda"])
+        O.ppo_update(pol, padam, d, clip_param=HP["clip_param"], ppo_epoch=c["ppo_epoch"], mini_batch_size=c["B_ppo"],
+                     value_loss_coef=HP["value_loss_coef"], max_grad_norm=HP["max_grad_norm"], logstd=HP["logstd"])
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_update()
+    times = [one_update() for _ in range(args.steps)]
+    dt = sum(times) / len(times)
+    v = T * N / dt
+    cfg = CONFIGS[args.config]
+    line = {"impl": "reference", "metric": "ppo_wdgail_update_env_steps_per_sec", "value": v, "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "T": cfg["T"], "N": cfg["N"], "B_ppo": cfg["B_ppo"], "B_gail": cfg["B_gail"],
+                       "ppo_epoch": cfg["ppo_epoch"], "gail_epoch": cfg["gail_epoch"]},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "one full update on " + c["workload"] + " (torch CPU fp32, all host threads); env-steps/s "
+                                       "is per-sample work so the bounded sample stands for the full workload"},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+LAUNCHES_PER_CALL = {"gc_conv_dgrad": 4, "gc_welford_merge": 2, "gc_small_linear_bwd": 2}
+
+
+class Profiler:
+    """Counts C-ABI calls (= our kernel launches) and, when armed, brackets every tensor-core contraction with CUDA
+    events on the launching stream, recording its algorithmic FLOPs."""
+
+    def __init__(self, A):
+        self.A, self.calls, self.launches, self.records, self.armed = A, 0, 0, [], False
+        self._orig = A.call
+        A.call = self._call
+
+    def _call(self, name, *args):
+        self.calls += 1
+        self.launches += LAUNCHES_PER_CALL.get(name, 1)
+        fl = self._flops(name, args) if self.armed else None
+        if fl is None:
+            return self._orig(name, *args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = self._orig(name, *args)
+        e1.record()
+        self.records.append((name, fl, e0, e1))
+        return r
+
+    @staticmethod
+    def _flops(name, a):
+        if name == "gc_conv_fprop" or name == "gc_conv_dgrad" or name == "gc_conv_wgrad":
+            g = a[0]._obj
+            return 2.0 * g.B * g.OH * g.OW * g.Cout * g.KH * g.KW * g.Cin
+        if name == "gc_linear_fwd":
+            return 2.0 * a[7] * a[8] * a[9]
+        if name == "gc_linear_dgrad":
+            return 2.0 * a[8] * a[9] * a[10]
+        if name == "gc_linear_wgrad":
+            return 2.0 * a[6] * a[7] * a[8]
+        return None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        by = {}
+        for name, fl, e0, e1 in self.records:
+            t = e0.elapsed_time(e1) * 1e-3
+            f, tt, n = by.get(name, (0.0, 0.0, 0))
+            by[name] = (f + fl, tt + t, n + 1)
+        tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
+        return by, tot_f, tot_t
+
+
+def hbm_microbench(A, dev, pk):
+    """GAE scan and fused PPO-loss kernels alone (BASELINE.json configs[1]: 16 envs x 2048 steps) plus the asymptotic
+    size where the launch is long enough for HBM bandwidth to be the bound; CUDA events, L2 flushed between launches."""
+    out = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, reps=10):
+        ts = []
+        for i in range(reps + 3):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+        return statistics.median(ts)
+
+    for T, N in ((2048, 16), (4096, 16384)):
+        r = torch.rand(T, N, 1, device=dev); v = torch.randn(T + 1, N, 1, device=dev); m = torch.ones(T + 1, N, 1, device=dev)
+        ret = torch.zeros_like(v)
+        t = timeit(lambda: A.gae_returns(r, v, m, ret, 0.99, 0.95))
+        b = 16.0 * T * N
+        out.append(dict(kernel="gae_scan", T=T, N=N, bytes=b, seconds=t, gbs=b / t / 1e9, frac=b / t / 1e9 / pk["hbm"]))
+        del r, v, m, ret
+    for B in (4096, 1 << 24):
+        head = torch.randn(B, 4, device=dev); act = torch.randn(B, 2, device=dev); s = [torch.randn(B, device=dev) for _ in range(3)]
+        stats = torch.tensor([0.0, float(B), float(B), 0.0], dtype=torch.float64, device=dev)
+        dh = torch.zeros(B, 4, device=dev); acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        t = timeit(lambda: A.ppo_loss(head, act, s[0], s[1], s[2], None, stats, dh, None, None, acc, B, HP["logstd"], True, 0.1, 0.5, 1.0, 0))
+        b = 48.0 * B + 4.0 * B   # 48 B/sample (log-prob fused) + the pad column of the [B,4] head rows
+        out.append(dict(kernel="ppo_loss_fwd_bwd", B=B, bytes=b, seconds=t, gbs=b / t / 1e9, frac=b / t / 1e9 / pk["hbm"]))
+        del head, act, s, dh
+    return out
+
+
+def cpu_baseline_sample():
+    """Oracle port timed on this box's host cores on a bounded sample (one update of configs[0]); rank 0, N=1 only."""
+    a = NS(warmup=0, steps=1, gpus=1, config="c1")
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run_reference(a)
+    line = json.loads(buf.getvalue().strip().splitlines()[-1])
+    return line["cpu_baseline"]
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import gail_carla_b200 as G
+    from gail_carla_b200 import _abi as A, synthetic
+    from gail_carla_b200.driver import update_iteration
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    A.load_library()
+    prof = Profiler(A)
+    pk = peaks()
+    c = dict(CONFIGS[args.config])
+    T, N_total = c["T"], c["N"]
+    if N_total % world or c["B_ppo"] % world or c["B_gail"] % world:
+        raise SystemExit(f"config {args.config} does not split over {world} ranks")
+    N = N_total // world                      # envs are sharded across ranks
+    Bp, Bg = c["B_ppo"] // world, c["B_gail"] // world
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+    torch.manual_seed(1)                      # identical replicas on every rank
+    pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False).to(dev)
+    agent = G.PPO(pol, HP["clip_param"], c["ppo_epoch"], Bp, HP["value_loss_coef"], dev, lr=HP["lr"], eps=HP["eps"],
+                  betas=HP["betas"], max_grad_norm=HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+    disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, dev, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
+                           HP["gail_max_grad_norm"]).to(dev)
+    ro = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=dev)
+    synthetic.fill_rollout(ro, seed=11 + rank, chunk=max(1, 4096 // N))
+    n_batches = (T * N) // Bg
+    loader = synthetic.SyntheticExpertLoader(n_batches, Bg, seed=21 + rank, pin=True)
+    torch.manual_seed(100 + rank)             # minibatch permutations / mix-up alphas differ per shard
+
+    def step():
+        return update_iteration(pol, agent, disc, ro, loader, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
+                                gail_epoch=c["gail_epoch"], bcgail=False, diagnostics=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = prof.launches
+    dt = timed(step, args.steps)
+    launches = prof.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    env_steps = T * N_total
+    value = env_steps * args.steps / dt
+
+    # ---- end-to-end: the rollout lives in pinned HOST memory (as tools/storage.py keeps it) and is uploaded every step
+    names = ("obs", "metrics", "actions", "action_log_probs", "value_preds", "masks")
+    host = {}
+    try:
+        for k in names:
+            host[k] = torch.empty(getattr(ro, k).shape, dtype=torch.float32, pin_memory=True)
+            host[k].copy_(getattr(ro, k))
+        pinned = True
+    except RuntimeError:
+        host = {k: getattr(ro, k).cpu() for k in names}
+        pinned = False
+    h2d = sum(v.numel() * 4 for v in host.values()) + sum(t.numel() * 4 for b in loader for t in b)
+    result_host = torch.empty(T, N, 1, dtype=torch.float32, pin_memory=True)
+
+    def step_e2e():
+        for k in names:
+            getattr(ro, k).copy_(host[k], non_blocking=True)
+        out = step()                                      # tuples are read back inside (one D2H per update call)
+        result_host.copy_(ro.returns[:-1], non_blocking=True)   # the step's result tensor back to the host
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    step_e2e()
+    dt_e2e = timed(step_e2e, args.steps)
+    e2e = env_steps * args.steps / dt_e2e
+    d2h = result_host.numel() * 4 + 8 * 15
+
+    # ---- instrumented step: per-contraction CUDA events -> tensor-pipe roofline of the dominant kernel
+    prof.armed = True
+    step()
+    prof.armed = False
+    by, tot_f, tot_t = prof.summary()
+    step_s = dt / args.steps
+    tf32_peak = pk["bf16"] / 2.0
+    roof = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05.mma.kind::tf32, all conv/linear contractions)",
+            "achieved": tot_f / tot_t / 1e12 if tot_t else None, "peak": tf32_peak, "unit": "TFLOP/s",
+            "frac": (tot_f / tot_t / 1e12) / tf32_peak if tot_t else None, "traffic": None,
+            "peak_note": f"TF32 dense = 1/2 of the {pk['src']} sustained bf16 peak ({pk['bf16']} TF/s); MEASURED_PEAKS.json has no TF32 entry",
+            "share_of_step": tot_t / step_s if step_s else None, "launches": len(prof.records),
+            "per_op": {k: {"tflops": v[0] / v[1] / 1e12, "seconds": v[1], "launches": v[2]} for k, v in by.items()}}
+
+    if rank == 0:
+        hbm = hbm_microbench(A, dev, pk) if world == 1 else None
+        cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
+        line = {"metric": "ppo_wdgail_update_env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+                "config": {"workload": c["workload"], "T": T, "N": N_total, "B_ppo": c["B_ppo"], "B_gail": c["B_gail"],
+                           "ppo_epoch": c["ppo_epoch"], "gail_epoch": c["gail_epoch"], "envs_per_rank": N,
+                           "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % (ro.obs.numel() * 4 / 1e9),
+                           "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce"},
+                "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                        "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

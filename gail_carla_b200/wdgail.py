@@ -1,0 +1,276 @@
+"""Drop-in for algo/wdgail.py ``Discriminator`` (tanh-Wasserstein critic with input-gradient penalty) on B200.
+
+Same constructor, ``update`` (7-tuple), ``compute_loss`` (3-tuple), ``predict_reward`` (CPU ``[N,1]`` tensor),
+``forward`` and ``compute_grad_pen``; state_dict keys ``obs_processor.main.{0,2,4,6}``,
+``metrics_processor.road_option_embedding``, ``trunk.{0,2}`` (algo/wdgail.py:19-38).
+
+``update`` runs expert, policy and mixed-up samples as ONE batch of 3B rows through the critic and never builds an
+autograd graph.  The penalty's double backward (algo/wdgail.py:85-97, ``create_graph=True``) is hand-derived: every
+non-linearity is piecewise linear, so with the LeakyReLU slope masks D_k frozen
+``g = dD/dx = C1^T D1 C2^T D2 C3^T D3 C4^T D4 W1a^T D5 w2^T`` is linear in each weight, and with ``u = d gp / d g``
+  d gp / d C_k = wgrad(delta_k, v_{k-1}),  d gp / d W1a = delta_5 (x) v_4,  d gp / d w2 = sum_b D5 W1a v_4,
+where delta_k is the ordinary dgrad chain seeded with 1 and ``v_k = D_k C_k v_{k-1}`` (v_0 = u) is a forward pass
+without biases.  Biases, the embedding and the metric/action columns of trunk.0 get exactly zero penalty gradient.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _abi as A
+from . import engine as E
+from ._abi import LDF, S2D_PER_SAMPLE, EPI_BIAS_LRELU, EPI_MASK, EPI_STORE
+from .model import _Holder, _conv_seq, N_METRIC_FEAT
+from .optim import FusedClipAdam
+from .running_mean_std import RunningMeanStd
+
+TAIL = N_METRIC_FEAT + 2      # metric features + action columns of trunk.0 (algo/wdgail.py:26-29)
+LDH = 128                     # row pitch of the hidden activations [rows, hidden_dim<=128]
+
+
+class CriticEngine:
+    def __init__(self, module: nn.Module, hidden: int):
+        if hidden > LDH or hidden % 4:
+            raise ValueError("hidden_dim must be a multiple of 4 and <= 128")
+        self.hidden = hidden
+        self.flat = E.FlatParams(module)
+        self.conv = E.ConvStack(self.flat, "obs_processor.", need_input_grad=True)
+        self.ws: Optional[E.Workspace] = None
+        self.w1 = None
+        self.dirty = True
+
+    def sync_params(self) -> None:
+        moved = self.flat.ensure()
+        dev = self.flat.flat.device
+        if dev.type != "cuda" and not getattr(A, "EMULATED", False):
+            raise RuntimeError("gail_carla_b200.Discriminator runs on CUDA only: move it to a CUDA device (no CPU fallback)")
+        if moved or self.dirty or self.w1 is None or self.w1.device != dev:
+            if self.w1 is None or self.w1.device != dev:
+                self.w1 = torch.zeros(self.hidden, LDF, dtype=torch.float32, device=dev)
+                self.dw1 = torch.zeros(self.hidden, LDF, dtype=torch.float32, device=dev)
+                self.ws = None
+            self.conv.prepare()
+            A.prep_fc1_weight(self.flat.p("trunk.0.weight"), self.w1, self.hidden, TAIL, LDF)
+            self.dirty = False
+
+    def workspace(self, rows: int) -> E.Workspace:
+        dev = self.flat.flat.device
+        if self.ws is None or self.ws.rows < rows or self.ws.device != dev:
+            self.ws = E.Workspace(dev, rows, with_input_grad=True)
+        return self.ws
+
+    # rows [row0,row0+B) <- images / metrics / actions given as dense rows or gathered by idx
+    def load_inputs(self, obs_rows, met_rows, act_rows, idx, B: int, row0: int) -> None:
+        ws = self.ws
+        A.gather_obs_s2d(obs_rows, idx, ws.X0[row0:], B)
+        A.gather_rows(met_rows, idx, ws.buf("metrics", ws.rows, 4)[row0:], B, 4, 4)
+        A.gather_rows(act_rows, idx, ws.buf("actions", ws.rows, 2)[row0:], B, 2, 2)
+
+    def tail_features(self, B: int, row0: int, mix_from: Optional[tuple] = None) -> None:
+        """ProcessMetrics + action passthrough into F[:, 25600:]; ``mix_from=(row_e,row_p,alpha)`` mixes the raw inputs."""
+        ws = self.ws
+        m, a = ws.buf("metrics", ws.rows, 4), ws.buf("actions", ws.rows, 2)
+        emb = self.flat.p("metrics_processor.road_option_embedding.weight")
+        out = ws.F[row0:, E.FEAT:]
+        if mix_from is None:
+            A.metrics_features(m[row0:], emb, out, LDF, 32, B, action=a[row0:])
+        else:
+            re, rp, alpha = mix_from
+            A.metrics_features(m[re:], emb, out, LDF, 32, B, action=a[re:], metrics2=m[rp:], action2=a[rp:], alpha=alpha)
+
+    def trunk_forward(self, rows: int) -> torch.Tensor:
+        """F[0:rows] -> hidden H (LeakyReLU) -> critic output d [rows]."""
+        ws, P = self.ws, self.flat.p
+        H = ws.buf("H", ws.rows, LDH)
+        E.linear_fwd(ws, "fc1d", ws.F, LDF, self.w1, LDF, P("trunk.0.bias"), H, LDH, rows, self.hidden, LDF, EPI_BIAS_LRELU)
+        d = ws.buf("d", ws.rows)
+        A.small_linear_fwd(H, LDH, P("trunk.2.weight"), P("trunk.2.bias"), d, 1, rows, 1, self.hidden)
+        return d
+
+    def forward(self, rows: int) -> torch.Tensor:
+        self.conv.forward(self.ws, rows)
+        return self.trunk_forward(rows)
+
+    def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0) -> None:
+        """Rows [0,B) expert, [B,2B) policy already loaded.  Builds the mix-up rows, runs forward + the full
+        backward (Wasserstein part + gradient penalty) and leaves the gradients in the flat buffer."""
+        ws, P, G, H_ = self.ws, self.flat.p, self.flat.g, self.hidden
+        R = 3 * B
+        # ---- forward over expert | policy | mix-up (algo/wdgail.py:116,121,66-82)
+        A.mixup(ws.X0, ws.X0[B:], alpha, ws.X0[2 * B:], B, S2D_PER_SAMPLE)
+        self.tail_features(B, 0); self.tail_features(B, B); self.tail_features(B, 2 * B, mix_from=(0, B, alpha))
+        d = self.forward(R)
+        dd = ws.buf("dd", ws.rows)
+        A.disc_loss_seed(d, dd, acc, B)                                   # acc[0:4]; seeds -/+tanh'/B and 1
+        # ---- backward
+        self.flat.grad.zero_()
+        dA = ws.grads()
+        H = ws.buf("H", ws.rows, LDH)
+        dH = ws.buf("dH", ws.rows, LDH)
+        A.small_linear_bwd(H, LDH, P("trunk.2.weight"), dd, 1, dH, LDH, G("trunk.2.weight"), G("trunk.2.bias"), R, 2 * B, 1,
+                           H_, E.SLOPE)
+        # delta_4 for all rows; metric/action columns only for the rows that carry loss (expert, policy)
+        A.linear_dgrad(dH, LDH, self.w1, LDF, dA[4], E.FEAT, R, E.FEAT, H_, mask_src=ws.F, ldm=LDF, slope=E.SLOPE)
+        A.linear_dgrad(dH, LDH, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, 2 * B, 32, H_)
+        m = ws.buf("metrics", ws.rows, 4)
+        emb_g = G("metrics_processor.road_option_embedding.weight")
+        A.metrics_features_bwd(m, ws.dFt, 32, emb_g, 2 * B)
+        self.conv.backward_data(ws, R)
+        # ---- gradient penalty: g = dD/dx on the mix-up rows, u = d gp/d g, second-order forward chain in place
+        self.conv.input_grad(ws, B, 2 * B)
+        A.grad_penalty(dA[0][2 * B:], ws.X0[2 * B:], acc[4:], B, S2D_PER_SAMPLE, lambda_, E.INV_STD)
+        self.conv.forward_masked(ws, B, 2 * B)
+        ws.F[2 * B:R, E.FEAT:].zero_()                                     # penalty gradient of the tail columns is 0
+        t = ws.buf("v5", ws.rows, LDH)
+        E.linear_fwd(ws, "fc1v", ws.F[2 * B:], LDF, self.w1, LDF, None, t, LDH, B, H_, LDF, EPI_STORE)
+        A.splitk_reduce(t, 1, B, H_, LDH, None, H[2 * B:], LDH, t, LDH, EPI_MASK, E.SLOPE)
+        A.colsum(t, LDH, B, H_, G("trunk.2.weight"))
+        # ---- weight gradients over all 3B rows ((delta, a) pairs for expert/policy, (delta_hat, v) for the penalty)
+        E.linear_wgrad(ws, "w1d", dH, LDH, ws.F, LDF, self.dw1, LDF, H_, LDF, R)
+        A.unprep_fc1_wgrad(self.dw1, 1, G("trunk.0.weight"), H_, TAIL, LDF)
+        A.colsum(dH, LDH, 2 * B, H_, G("trunk.0.bias"))
+        self.conv.backward_params(ws, R, 2 * B)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, state_shape, metrics_space, action_space, hidden_dim, device, lr, eps, betas, max_grad_norm=None):
+        super(Discriminator, self).__init__()
+        if tuple(state_shape) != (3, 192, 192) or metrics_space.shape[0] != 4 or action_space.shape[0] != 2:
+            raise ValueError("Discriminator supports state (3,192,192), metrics (4,), action (2,)")
+        self.device = device
+        self.obs_processor = _Holder(main=_conv_seq())
+        self.metrics_processor = _Holder(road_option_embedding=nn.Embedding(10, 8))
+        self.trunk = nn.Sequential(nn.Linear(E.FEAT + TAIL, hidden_dim), nn.LeakyReLU(E.SLOPE), nn.Linear(hidden_dim, 1))
+        self.hidden_dim = hidden_dim
+        self.max_grad_norm = max_grad_norm
+        self._engine: Optional[CriticEngine] = None
+        self.optimizer = FusedClipAdam(lambda: self.engine.flat, self.parameters(), lr, eps, betas, max_grad_norm)
+        self.returns = None
+        self.ret_rms = RunningMeanStd(shape=())     # constructed and never used, as in algo/wdgail.py:37-38
+
+    @property
+    def engine(self) -> CriticEngine:
+        if self._engine is None:
+            self._engine = CriticEngine(self, self.hidden_dim)
+        return self._engine
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        if self._engine is not None:
+            self._engine.dirty = True
+        return r
+
+    def _dev(self):
+        return self.engine.flat.flat.device
+
+    def _to_dev(self, *ts):
+        dev = self._dev()
+        return [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in ts]
+
+    # ---- algo/wdgail.py:40-54 (forward only; gp=True has no meaning without autograd)
+    def forward(self, state, metrics, action, gp=False):
+        if gp:
+            raise NotImplementedError("the autograd handles of forward(gp=True) do not exist here; use compute_grad_pen")
+        with torch.no_grad():
+            eng = self.engine
+            eng.sync_params()
+            state, metrics, action = self._to_dev(state, metrics, action)
+            B = state.shape[0]
+            eng.workspace(B)
+            eng.load_inputs(state, metrics, action, None, B, 0)
+            eng.tail_features(B, 0)
+            return eng.forward(B)[:B].clone().view(B, 1)
+
+    # ---- algo/wdgail.py:56-98 (value only; alpha drawn from the CPU default generator like the reference)
+    def compute_grad_pen(self, expert_state, expert_metrics, expert_action, policy_state, policy_metrics, policy_action,
+                         lambda_=10):
+        with torch.no_grad():
+            eng = self.engine
+            eng.sync_params()
+            B = expert_state.shape[0]
+            alpha = torch.rand(B, 1, 1, 1).view(B).to(self._dev())
+            eng.workspace(3 * B)
+            eng.load_inputs(*self._to_dev(expert_state, expert_metrics, expert_action), None, B, 0)
+            eng.load_inputs(*self._to_dev(policy_state, policy_metrics, policy_action), None, B, B)
+            acc = torch.zeros(8, dtype=torch.float64, device=self._dev())
+            eng.update_step(B, alpha, acc, float(lambda_))
+            return (float(lambda_) * acc[4] / B).float()
+
+    # ---- algo/wdgail.py:100-147
+    def update(self, expert_loader, rollouts):
+        eng = self.engine
+        eng.sync_params()
+        dev = self._dev()
+        B = expert_loader.batch_size
+        obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
+        acc = torch.zeros(8, dtype=torch.float64, device=dev)
+        n = 0
+        with torch.no_grad():
+            for expert_batch, idx in zip(expert_loader, rollouts.minibatch_indices(B)):
+                e_obs, e_met, e_act = self._to_dev(*expert_batch)
+                if e_obs.shape[0] != B:
+                    raise ValueError("expert batches must all have expert_loader.batch_size rows (drop_last=True)")
+                eng.workspace(3 * B)
+                eng.load_inputs(e_obs, e_met, e_act, None, B, 0)
+                eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
+                alpha = torch.rand(B, 1, 1, 1).view(B)            # algo/wdgail.py:66 - CPU default generator
+                alpha = alpha.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else alpha
+                eng.update_step(B, alpha, acc)
+                self.optimizer.step()
+                eng.dirty = True
+                eng.sync_params()
+                n += B
+        s_de, s_dp, s_te, s_tp, s_gp = acc[:5].cpu().tolist()   # single read-back per update
+        wd = s_te - s_tp
+        gp = 10.0 * s_gp
+        return (-wd + gp) / n, s_dp / n, s_de / n, wd / n, gp / n, s_te / n, s_tp / n
+
+    # ---- algo/wdgail.py:149-179
+    def compute_loss(self, expert_loader, rollouts, batch_size=None):
+        eng = self.engine
+        eng.sync_params()
+        dev = self._dev()
+        B = expert_loader.batch_size
+        obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
+        acc = torch.zeros(8, dtype=torch.float64, device=dev)
+        n = 0
+        with torch.no_grad():
+            for expert_batch, idx in zip(expert_loader, rollouts.minibatch_indices(B, batch_size)):
+                eng.workspace(3 * B)
+                eng.load_inputs(*self._to_dev(*expert_batch), None, B, 0)
+                eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
+                eng.tail_features(B, 0); eng.tail_features(B, B)
+                d = eng.forward(2 * B)
+                A.disc_loss_seed(d, eng.ws.buf("dd", eng.ws.rows), acc, B)     # only the tanh sums are used here
+                n += B
+        _, _, s_te, s_tp = acc[:4].cpu().tolist()
+        if n == 0:
+            return 0, 0, 0
+        return (s_te - s_tp) / n, s_te / n, s_tp / n
+
+    # ---- algo/wdgail.py:181-189 (gamma, masks, update_rms are ignored by the reference, so also here)
+    def predict_reward(self, state, metrics, action, gamma, masks, update_rms=True):
+        with torch.no_grad():
+            d = self.forward(state, metrics, action)
+            r = torch.empty_like(d)
+            A.reward_epilogue(d, r, d.numel())
+            return r.cpu()
+
+    def predict_rewards_rollout(self, rollouts, chunk: int = 4096) -> None:
+        """tools/learn.py:196-202 as one batched pass: gail_rewards[t, n] for every stored step, written in HBM."""
+        eng = self.engine
+        eng.sync_params()
+        T, N = rollouts.num_steps, rollouts.num_processes
+        obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
+        out = rollouts.gail_rewards.view(-1)
+        idx_all = torch.arange(T * N, device=self._dev())
+        with torch.no_grad():
+            for s in range(0, T * N, chunk):
+                B = min(chunk, T * N - s)
+                eng.workspace(B)
+                eng.load_inputs(obs_rows, met_rows, act_rows, idx_all[s:s + B], B, 0)
+                eng.tail_features(B, 0)
+                d = eng.forward(B)
+                A.reward_epilogue(d, out[s:], B)

@@ -77,6 +77,7 @@ def _head_tail(head, actions, logstd, activation):
     return v, mu0, mu1, logp
 
 
+@torch.enable_grad()
 def ppo_loss(head_out, actions, old_logp, value_old, returns, adv, adv_stats_, d_head, out_value, out_logp, loss_acc, B,
              logstd, activation, clip, value_coef, action_weight, mode):
     h = head_out.view(-1, 4)[:B].detach().clone().requires_grad_(mode != 2)
@@ -350,8 +351,9 @@ def conv_wgrad(geom, dy, x, dw_partial, splits):
     g = geom
     xin = _in_view(g, x)[:, :g.H, :g.W].permute(0, 3, 1, 2)
     d = _out_view(g, dy)[:, :g.OH, :g.OW].permute(0, 3, 1, 2)
-    w = torch.zeros(g.Cout, g.Cin, g.KH, g.KW, requires_grad=True)
-    (F.conv2d(xin, w, None, stride=g.S)[:, :, :g.OH, :g.OW] * d).sum().backward()
+    with torch.enable_grad():
+        w = torch.zeros(g.Cout, g.Cin, g.KH, g.KW, requires_grad=True)
+        (F.conv2d(xin, w, None, stride=g.S)[:, :, :g.OH, :g.OW] * d).sum().backward()
     n = g.Cout * g.KH * g.KW * g.Cin
     p = dw_partial.view(-1)[:splits * n].view(splits, n)
     p.zero_()

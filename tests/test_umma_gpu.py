@@ -1,0 +1,64 @@
+"""GPU parity of the tcgen05 implicit-GEMM engine, op by op, through the C ABI.
+
+Integer-valued inputs are exact in TF32, so those cases must match the CPU statement (oracle/abi_emu.py) bit for bit
+in value: any mismatch is a descriptor / layout bug.  Random fp32 inputs check the TF32 rounding level:
+relative Frobenius error <= 2e-3 (TF32 has a 10-bit mantissa; TMA converts fp32->tf32 round-to-nearest)."""
+import pytest
+import torch
+
+import gpu_probe_umma as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", P.CASES)
+def test_contraction_exact_on_integers(case):
+    assert P.run_case(case)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (384, 100, 25632), (130, 3 * 32, 100)])
+def test_linear_tf32_rounding_level(M, N, K):
+    from gail_carla_b200 import _abi as A
+    g = torch.Generator().manual_seed(M + N + K)
+    ld = (K + 3) // 4 * 4
+    x = torch.zeros(M, ld); x[:, :K] = torch.randn(M, K, generator=g)
+    w = torch.zeros(N, ld); w[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    ldy = (N + 3) // 4 * 4
+    y = torch.zeros(M, ldy, device="cuda")
+    A.linear_fwd(x.cuda(), ld, w.cuda(), ld, b.cuda(), y, ldy, M, N, K, A.EPI_BIAS, 0.2, 1)
+    ref = x[:, :K].double() @ w[:, :K].double().t() + b.double()
+    rel = ((y[:, :N].cpu().double() - ref).norm() / ref.norm()).item()
+    assert rel < 2e-3, rel
+
+
+def test_conv_stack_tf32_vs_fp64():
+    """conv1..conv4 forward through the engine vs torch fp64 conv on the same normalised input."""
+    import torch.nn.functional as F
+    from gail_carla_b200 import _abi as A, engine as E
+    g = torch.Generator().manual_seed(3)
+    B = 3
+    obs = torch.rand(B, 3, 192, 192, generator=g)
+    x0 = torch.zeros(B, 96 * 96 * 16, device="cuda")
+    A.gather_obs_s2d(obs.cuda(), None, x0, B)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1); std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    ref = ((obs - mean) / std).double()
+    acts = [x0, torch.zeros(B, 96 * 96 * 32, device="cuda"), torch.zeros(B, 46 * 46 * 64, device="cuda"),
+            torch.zeros(B, 22 * 22 * 128, device="cuda"), torch.zeros(B, A.LDF, device="cuda")]
+    for i in range(1, 5):
+        cin, cout = E.CONV_CH[i - 1], E.CONV_CH[i]
+        w = torch.randn(cout, cin, 4, 4, generator=g) / (cin * 16) ** 0.5; b = torch.randn(cout, generator=g) * 0.1
+        n = 2048 if i == 1 else cout * cin * 16
+        wf = torch.zeros(n, device="cuda")
+        A.prep_conv_weight(w.cuda(), wf, None, cout, cin, i == 1)
+        A.conv_fprop(E.conv_geom(i, B), acts[i - 1], wf, b.cuda(), acts[i], A.EPI_BIAS_LRELU, 0.2)
+        ref = F.leaky_relu(F.conv2d(ref, w.double(), b.double(), stride=2), 0.2)
+        if i == 1:
+            got = acts[1].view(B, 96, 96, 32)[:, :95, :95].permute(0, 3, 1, 2)
+        elif i == 4:
+            got = acts[4][:, :25600].view(B, 10, 10, 256).permute(0, 3, 1, 2)
+        else:
+            s = ref.shape[-1]
+            got = acts[i].view(B, s, s, cout).permute(0, 3, 1, 2)
+        rel = ((got.cpu().double() - ref).norm() / ref.norm()).item()
+        assert rel < 3e-3, (i, rel)
