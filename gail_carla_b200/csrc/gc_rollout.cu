@@ -4,6 +4,9 @@
 //   * fused PPO loss forward+backward on the head outputs   (tools/model.py:45-53,80-85; algo/ppo.py:80-85,104-113)
 //   * Welford/Chan running mean-var merge                   (common/running_mean_std.py:10-31)
 // All kernels enqueue on the caller's stream, never synchronise, and borrow their pointers.
+#include <algorithm>
+#include <cstdlib>
+
 #include "gc_common.cuh"
 #include "../../include/gail_carla_b200.h"
 
@@ -71,27 +74,39 @@ __global__ void __launch_bounds__(512) gae_scan_kernel(const float* __restrict__
     }
     if (c < C) { sA[c * NB + nl] = A; sB[c * NB + nl] = B; }
     __syncthreads();
-    // suffix scan over chunks, one warp per env, lanes over chunks (blocks of 32 chunks, high to low)
-    for (int e = warp; e < NB; e += nwarps) {
-      float carry = sIn[e];
-      for (int cb = (C + 31) / 32 - 1; cb >= 0; --cb) {
-        const int ci = cb * 32 + lane;
-        float a = ci < C ? sA[ci * NB + e] : 1.f;
-        float b = ci < C ? sB[ci * NB + e] : 0.f;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {  // inclusive suffix composition f_lane o f_{lane+1} o ...
-          const float a2 = __shfl_down_sync(0xffffffffu, a, off);
-          const float b2 = __shfl_down_sync(0xffffffffu, b, off);
-          if (lane + off < 32) { b = a * b2 + b; a = a * a2; }
+    if (C <= 8) {
+      // few chunks: one thread per env folds them serially (latest chunk first)
+      if (tid < NB) {
+        float carry = sIn[tid];
+        for (int ci = C - 1; ci >= 0; --ci) {
+          sCarry[ci * NB + tid] = carry;
+          carry = sA[ci * NB + tid] * carry + sB[ci * NB + tid];
         }
-        const float an = __shfl_down_sync(0xffffffffu, a, 1);
-        const float bn = __shfl_down_sync(0xffffffffu, b, 1);
-        const float mine = lane < 31 ? an * carry + bn : carry;  // gae entering chunk ci
-        if (ci < C) sCarry[ci * NB + e] = mine;
-        const float a0 = __shfl_sync(0xffffffffu, a, 0), b0 = __shfl_sync(0xffffffffu, b, 0);
-        carry = a0 * carry + b0;
+        sIn[tid] = carry;
       }
-      if (lane == 0) sIn[e] = carry;
+    } else {
+      // suffix scan over chunks, one warp per env, lanes over chunks (blocks of 32 chunks, high to low)
+      for (int e = warp; e < NB; e += nwarps) {
+        float carry = sIn[e];
+        for (int cb = (C + 31) / 32 - 1; cb >= 0; --cb) {
+          const int ci = cb * 32 + lane;
+          float a = ci < C ? sA[ci * NB + e] : 1.f;
+          float b = ci < C ? sB[ci * NB + e] : 0.f;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {  // inclusive suffix composition f_lane o f_{lane+1} o ...
+            const float a2 = __shfl_down_sync(0xffffffffu, a, off);
+            const float b2 = __shfl_down_sync(0xffffffffu, b, off);
+            if (lane + off < 32) { b = a * b2 + b; a = a * a2; }
+          }
+          const float an = __shfl_down_sync(0xffffffffu, a, 1);
+          const float bn = __shfl_down_sync(0xffffffffu, b, 1);
+          const float mine = lane < 31 ? an * carry + bn : carry;  // gae entering chunk ci
+          if (ci < C) sCarry[ci * NB + e] = mine;
+          const float a0 = __shfl_sync(0xffffffffu, a, 0), b0 = __shfl_sync(0xffffffffu, b, 0);
+          carry = a0 * carry + b0;
+        }
+        if (lane == 0) sIn[e] = carry;
+      }
     }
     __syncthreads();
     if (live) {
@@ -318,13 +333,21 @@ int gc_gae_returns(const float* gail_rewards, const float* value_preds, const fl
   GC_REQUIRE(T > 0 && N > 0, "gc_gae_returns: T=%d N=%d must be positive", T, N);
   GC_REQUIRE(gail_rewards && value_preds && masks && returns, "gc_gae_returns: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int NB = N >= 32 ? 32 : N;
+  // Launch shape.  Few envs: one CTA covers them all and many time chunks run in parallel (short serial chain).
+  // Many envs: wide env groups per CTA (long contiguous row segments), few chunks, enough CTAs for every SM.
+  int NB = N >= 32 ? 32 : N, threads = 512, L = 16;
+  if (N >= 128 * gc::kNumSMs) { NB = 128; threads = 256; L = 8; }
+  else if (N >= 64 * gc::kNumSMs) { NB = 64; threads = 256; L = 8; }
+  else if (N >= 32 * 2 * gc::kNumSMs) { NB = 32; threads = 256; L = 8; }
+  if (const char* cfg = getenv("GC_GAE_CFG")) {  // tuning override: "NB,threads,L"
+    int a = 0, b = 0, c = 0;
+    if (sscanf(cfg, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && a <= N && b >= a && b <= 512 && (c == 4 || c == 8 || c == 16)) {
+      NB = a; threads = b; L = c;
+    }
+  }
   const int grid = (N + NB - 1) / NB;
-  // many CTAs: small blocks keep more loads in flight per SM; few CTAs: big blocks shorten the serial chain
-  int threads = grid >= 2 * gc::kNumSMs ? 256 : 512;
   int C = threads / NB;
-  int L = 16;
-  if ((long)C * 8 >= T) L = 8;
+  if ((long)C * 8 >= T && L > 8) L = 8;
   if ((long)C * 4 >= T) L = 4;
   // do not spawn chunks that would be entirely before t=0
   const int c_needed = (T + L - 1) / L;
@@ -374,7 +397,7 @@ int gc_ppo_loss_fwd_bwd(const float* head_out, const float* actions, const float
   if (mode == 0) GC_REQUIRE(old_logp && value_old && returns && (adv || adv_stats) && d_head_out,
                             "gc_ppo_loss_fwd_bwd: PPO mode needs old_logp, value_old, returns, adv|adv_stats, d_head_out");
   if (mode == 1) GC_REQUIRE(d_head_out, "gc_ppo_loss_fwd_bwd: BC mode needs d_head_out");
-  const int grid = std::min((B + 255) / 256, 4 * gc::kNumSMs);
+  const int grid = std::min((B + 255) / 256, 16 * gc::kNumSMs);
   ppo_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)head_out, (const float2*)actions, old_logp, value_old, returns, adv, adv_stats, (float4*)d_head_out,
       out_value, out_logp, loss_acc, B, logstd0, logstd1, activation, clip, value_coef, action_weight, 1.0f / (float)B, mode);

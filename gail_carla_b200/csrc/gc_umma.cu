@@ -133,27 +133,25 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
   p.b_bytes = (p.b_bytes + 1023) & ~1023;
   p.nbuf = p.epilogue == EPI_MASK ? 4 : 2;
-  p.tmem_cols = pow2_cols(bpan * 32);
+  p.tmem_cols = pow2_cols(2 * bpan * 32);  // two accumulator stages
   p.d_row_bytes = p.bn >= 32 ? 128 : p.bn * 4;
   const int stage = p.a_bytes + p.b_bytes;
   const int fixed = p.nbuf * 16384 + 2048;
   int stages = (kSmemBudget - fixed) / stage;
   stages = std::min(stages, 8);
-  stages = std::min(stages, std::max(2, p.k_iters));
   GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B)", what, stage);
-  // short K loops: prefer two co-resident CTAs per SM (one's epilogue overlaps the other's mainloop)
-  if (p.k_iters <= 96) {
-    const int half = (kSmemBudget / 2 - 1024 - fixed) / stage;
-    if (half >= 2) stages = std::min(stages, std::min(half, 4));
-  }
   p.stages = stages;
+  p.mt = pl.grid.x; p.nt = pl.grid.y; p.zt = pl.grid.z;
+  const long total_tiles = (long)p.mt * p.nt * p.zt;
+  GC_REQUIRE(total_tiles > 0 && total_tiles < (1L << 31), "%s: bad tile count", what);
+  const dim3 grid((unsigned)std::min<long>(total_tiles, gc::kNumSMs), 1, 1);
   const size_t smem = (size_t)stages * stage + fixed;
   auto launch = [&](auto kern) -> int {
     static thread_local const void* configured[3] = {nullptr, nullptr, nullptr};
     (void)configured;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    kern<<<pl.grid, 192, smem, st>>>(p);
+    kern<<<grid, 192, smem, st>>>(p);
     return gc::launch_status(what);
   };
   if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false>);

@@ -32,6 +32,7 @@ enum Epilogue { EPI_STORE = 0, EPI_BIAS_LRELU = 1, EPI_BIAS = 2, EPI_MASK = 3 };
 struct alignas(64) GemmParams {
   CUtensorMap mapA, mapB, mapD, mapX;
   TmaAddr a, b, d;
+  int mt, nt, zt;      // tile grid: m-tiles x n-tiles x z (persistent CTAs walk tile = (z*nt + n)*mt + m)
   int e0, e1;          // m-tile index -> (m0, m1, m2) extents
   int f0;              // n-tile index -> (n0, n1)
   int g0, g1;          // k-iteration -> (k0, k1, k2)

@@ -103,27 +103,57 @@ __device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc],
 }
 
 // ------------------------------------------------------------------ the kernel
-// warps 0-3: epilogue (TMEM lanes 32w..32w+31) | warp 4: TMA producer + TMEM owner | warp 5: MMA issuer
+__device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int (&src)[kSrc], int& n_tile) {
+  const int mt = tile % p.mt;
+  const int r = tile / p.mt;
+  n_tile = r % p.nt;
+  src[M0] = mt % p.e0;
+  const int t = mt / p.e0;
+  src[M1] = t % p.e1;
+  src[M2] = t / p.e1;
+  src[N0] = n_tile % p.f0;
+  src[N1] = n_tile / p.f0;
+  src[K0] = src[K1] = src[K2] = 0;
+  src[Z] = r / p.nt;
+}
+
+__device__ __forceinline__ void tile_coords(const TmaAddr& t, const int (&src)[kSrc], int (&c)[5]) {
+#pragma unroll
+  for (int d = 0; d < 5; ++d) c[d] = t.off[d];
+  coords(t, src, 0, 5, c);
+  coords(t, src, Z, Z + 1, c);
+}
+
+// Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+//   warp 4  : TMA producer (one lane) + TMEM owner          -> smem ring (full/empty mbarriers)
+//   warp 5  : tcgen05.mma issuer (one lane)                 -> two TMEM accumulator stages (tmem_full/tmem_empty)
+//   warps 0-3: epilogue, TMEM lanes 32w..32w+31             -> staging smem -> TMA store
+// so the epilogue of tile i overlaps the mainloop of tile i+1 and barrier/TMEM set-up is paid once per SM.
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;  // 2 x 16 KB, 1024-aligned
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;  // nbuf x 16 KB, 1024-aligned
   uint64_t* bars = (uint64_t*)(staging + (size_t)p.nbuf * 16384);
-  // bars: full[stages], empty[stages], tmem_full, aux[4]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 5);
+  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], aux[4]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
-  const uint32_t tmem_full = empty0 + 8 * p.stages, aux0 = tmem_full + 8;
+  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16, aux0 = tempty0 + 16;
+  const int total_tiles = p.mt * p.nt * p.zt;
+  const int acc_cols = ((p.bn + 31) >> 5) << 5;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
+    }
     for (int q = 0; q < 4; ++q) mbar_init(aux0 + 8 * q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
@@ -139,55 +169,41 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile-constant coordinate sources
-  int src[kSrc];
-  {
-    const int mt = blockIdx.x;
-    src[M0] = mt % p.e0;
-    const int t = mt / p.e0;
-    src[M1] = t % p.e1;
-    src[M2] = t / p.e1;
-    src[N0] = blockIdx.y % p.f0;
-    src[N1] = blockIdx.y / p.f0;
-    src[K0] = src[K1] = src[K2] = 0;
-    src[Z] = blockIdx.z;
-  }
-
   if (warp == 4) {
     if (lane == 0) {
-      int baseA[5], baseB[5];
-#pragma unroll
-      for (int d = 0; d < 5; ++d) { baseA[d] = p.a.off[d]; baseB[d] = p.b.off[d]; }
-      coords(p.a, src, 0, 5, baseA);
-      coords(p.b, src, 0, 5, baseB);
-      coords(p.a, src, Z, Z + 1, baseA);
-      coords(p.b, src, Z, Z + 1, baseB);
       const uint32_t tx = p.a_panels * p.a_panel_bytes + p.b_panels * p.b_panel_bytes;
-      for (int it = 0; it < p.k_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(full0 + 8 * s, tx);
-        const int kit = it + blockIdx.z * p.kz_stride;
-        src[K0] = kit % p.g0;
-        const int t = kit / p.g0;
-        src[K1] = t % p.g1;
-        src[K2] = t / p.g1;
-        int ca[5], cb[5];
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int src[kSrc], n_tile, baseA[5], baseB[5];
+        decode_tile(p, tile, src, n_tile);
+        tile_coords(p.a, src, baseA);
+        tile_coords(p.b, src, baseB);
+        for (int k = 0; k < p.k_iters; ++k, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          mbar_expect_tx(full0 + 8 * s, tx);
+          const int kit = k + src[Z] * p.kz_stride;
+          src[K0] = kit % p.g0;
+          const int t = kit / p.g0;
+          src[K1] = t % p.g1;
+          src[K2] = t / p.g1;
+          int ca[5], cb[5];
 #pragma unroll
-        for (int d = 0; d < 5; ++d) { ca[d] = baseA[d]; cb[d] = baseB[d]; }
-        coords(p.a, src, K0, K2 + 1, ca);
-        coords(p.b, src, K0, K2 + 1, cb);
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
-        for (int q = 0; q < p.a_panels; ++q) {
-          tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, ca);
+          for (int d = 0; d < 5; ++d) { ca[d] = baseA[d]; cb[d] = baseB[d]; }
+          coords(p.a, src, K0, K2 + 1, ca);
+          coords(p.b, src, K0, K2 + 1, cb);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+          for (int q = 0; q < p.a_panels; ++q) {
+            tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, ca);
 #pragma unroll
-          for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
-        }
-        for (int q = 0; q < p.b_panels; ++q) {
-          tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
+            for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
+          }
+          for (int q = 0; q < p.b_panels; ++q) {
+            tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
 #pragma unroll
-          for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+            for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+          }
         }
       }
     }
@@ -200,107 +216,120 @@ __global__ void __launch_bounds__(192) umma_gemm_kernel(const __grid_constant__ 
       const int ksteps = p.bk >> 3;
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.b_panel_bytes : 0u;
-      for (int it = 0; it < p.k_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(full0 + 8 * s, ph);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int acc = ti & 1;
+        mbar_wait(tempty0 + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, A_MN ? 512 : 1024, A_MN ? 1 : 2);
-          const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
-          umma_tf32(tmem_base, ad, bd, idesc, (it | ks) ? 1u : 0u);
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * acc_cols);
+        for (int k = 0; k < p.k_iters; ++k, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+            const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
+            umma_tf32(tacc, ad, bd, idesc, (k | ks) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+        umma_commit(tfull0 + 8 * acc);
       }
-      umma_commit(tmem_full);
     }
     __syncwarp();
   } else {
     // ---------------- epilogue: thread t owns accumulator row 32*warp + lane ----------------
-    // Output goes out in 32-column panels through `nbuf` 16 KB staging buffers.  With EPI_MASK the panel's
-    // LeakyReLU' source tile (same box geometry as the output) is TMA-loaded into the staging buffer two
-    // panels ahead, multiplied in place and stored from the same buffer.
+    // Output leaves in 32-column panels through `nbuf` 16 KB staging buffers (a ring over all panels of all tiles
+    // of this CTA).  With EPI_MASK the panel's LeakyReLU' source tile (same box geometry as the output) is
+    // TMA-loaded into the staging buffer two panels ahead, multiplied in place and stored from the same buffer.
     const int row = warp * 32 + lane;
     const int n_panels = (p.bn + 31) >> 5;
     const bool swz = p.d_row_bytes == 128;
     const bool masked = p.epilogue == EPI_MASK;
     const int nbuf = p.nbuf;
-    int cd[5];
+    int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (thread 0 only)
+    auto prefetch_one = [&]() {
+      if (pf_tile >= total_tiles) return;
+      int src[kSrc], nt, cx[5];
+      decode_tile(p, pf_tile, src, nt);
+      tile_coords(p.d, src, cx);
 #pragma unroll
-    for (int d = 0; d < 5; ++d) cd[d] = p.d.off[d];
-    coords(p.d, src, 0, 5, cd);
-    coords(p.d, src, Z, Z + 1, cd);
-    if (masked && threadIdx.x == 0) {  // prefetch mask tiles of panels 0 and 1 while the mainloop runs
-      for (int q = 0; q < 2 && q < n_panels; ++q) {
-        int cx[5];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) cx[d] = cd[d] + q * p.d.panel[d];
-        mbar_expect_tx(aux0 + 8 * q, (uint32_t)p.d_box_bytes);
-        tma_load_5d(smem_u32(staging + q * 16384), &p.mapX, aux0 + 8 * q, cx);
-      }
-    }
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    for (int q = 0; q < n_panels; ++q) {
-      uint8_t* buf = staging + (q % nbuf) * 16384;
-      if (threadIdx.x == 0 && q >= 2) {
-        tma_wait_read<1>();  // store of panel q-2 has drained its staging buffer
-      }
-      if (masked && threadIdx.x == 0 && q + 2 < n_panels) {
-        // buffer (q+2)%4 was last read by the store of panel q-2 (drained above); fetch mask tile q+2 into it
-        const int j = (q + 2) % nbuf;
-        int cx[5];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) cx[d] = cd[d] + 2 * p.d.panel[d];
-        mbar_expect_tx(aux0 + 8 * j, (uint32_t)p.d_box_bytes);
-        tma_load_5d(smem_u32(staging + j * 16384), &p.mapX, aux0 + 8 * j, cx);
-      }
-      epi_bar_sync();
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 32), v);
-      const int col0 = blockIdx.y * p.bn + q * 32;
-      if (p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float b = (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
-          const float x = v[j] + b;
-          v[j] = (p.epilogue == EPI_BIAS_LRELU) ? gc::leaky(x, p.slope) : x;
+      for (int d = 0; d < 5; ++d) cx[d] += pf_q * p.d.panel[d];
+      const int j = pf_count % nbuf;
+      mbar_expect_tx(aux0 + 8 * j, (uint32_t)p.d_box_bytes);
+      tma_load_5d(smem_u32(staging + j * 16384), &p.mapX, aux0 + 8 * j, cx);
+      ++pf_count;
+      if (++pf_q == n_panels) { pf_q = 0; pf_tile += gridDim.x; }
+    };
+    if (masked && threadIdx.x == 0) { prefetch_one(); prefetch_one(); }
+    int pc = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int src[kSrc], n_tile, cd[5];
+      decode_tile(p, tile, src, n_tile);
+      tile_coords(p.d, src, cd);
+      const int acc = ti & 1;
+      mbar_wait(tfull0 + 8 * acc, (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_cols);
+      for (int q = 0; q < n_panels; ++q, ++pc) {
+        uint8_t* buf = staging + (pc % nbuf) * 16384;
+        if (threadIdx.x == 0) {
+          if (pc >= 2) tma_wait_read<1>();  // the store of panel pc-2 has drained its staging buffer
+          if (masked) prefetch_one();       // panel pc+2 -> buffer (pc+2)%4, free since the wait above
         }
-      }
-      const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
-      const int nchunk = p.d_row_bytes >> 4;
-      if (masked) {
-        mbar_wait(aux0 + 8 * (q % nbuf), (q / nbuf) & 1);
+        epi_bar_sync();
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)(q * 32), v);
+        if (q == n_panels - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+        }
+        const int col0 = n_tile * p.bn + q * 32;
+        if (p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float b = (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
+            const float x = v[j] + b;
+            v[j] = (p.epilogue == EPI_BIAS_LRELU) ? gc::leaky(x, p.slope) : x;
+          }
+        }
+        const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
+        const int nchunk = p.d_row_bytes >> 4;
+        if (masked) {
+          mbar_wait(aux0 + 8 * (pc % nbuf), (pc / nbuf) & 1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < nchunk) {
+              uint32_t o = rbase + j * 16;
+              if (swz) o ^= ((o >> 7) & 7) << 4;
+              const float4 m = *reinterpret_cast<const float4*>(buf + o);
+              v[4 * j + 0] *= m.x > 0.f ? 1.f : p.slope;
+              v[4 * j + 1] *= m.y > 0.f ? 1.f : p.slope;
+              v[4 * j + 2] *= m.z > 0.f ? 1.f : p.slope;
+              v[4 * j + 3] *= m.w > 0.f ? 1.f : p.slope;
+            }
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j < nchunk) {
             uint32_t o = rbase + j * 16;
             if (swz) o ^= ((o >> 7) & 7) << 4;
-            const float4 m = *reinterpret_cast<const float4*>(buf + o);
-            v[4 * j + 0] *= m.x > 0.f ? 1.f : p.slope;
-            v[4 * j + 1] *= m.y > 0.f ? 1.f : p.slope;
-            v[4 * j + 2] *= m.z > 0.f ? 1.f : p.slope;
-            v[4 * j + 3] *= m.w > 0.f ? 1.f : p.slope;
+            *reinterpret_cast<float4*>(buf + o) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           }
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (j < nchunk) {
-          uint32_t o = rbase + j * 16;
-          if (swz) o ^= ((o >> 7) & 7) << 4;
-          *reinterpret_cast<float4*>(buf + o) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_async_smem();
+        epi_bar_sync();
+        if (threadIdx.x == 0) {
+          tma_store_5d(&p.mapD, smem_u32(buf), cd);
+          tma_commit();
         }
-      }
-      fence_async_smem();
-      epi_bar_sync();
-      if (threadIdx.x == 0) {
-        tma_store_5d(&p.mapD, smem_u32(buf), cd);
-        tma_commit();
-      }
 #pragma unroll
-      for (int d = 0; d < 5; ++d) cd[d] += p.d.panel[d];
+        for (int d = 0; d < 5; ++d) cd[d] += p.d.panel[d];
+      }
     }
     if (threadIdx.x == 0) tma_wait_read<0>();
   }

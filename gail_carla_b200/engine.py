@@ -136,6 +136,29 @@ class Workspace:
         return t
 
 
+_SHARED: Dict[str, Workspace] = {}
+
+
+def shared_workspace(device, rows: int, with_input_grad: bool) -> Workspace:
+    """One activation / gradient workspace per device, shared by the policy and the critic (their updates never
+    overlap in time), grown on demand.  At B=4096 the critic's 3B-row workspace is ~70 GB, so sharing matters."""
+    key = str(device)
+    ws = _SHARED.get(key)
+    if ws is None or ws.rows < rows:
+        if ws is not None:
+            _SHARED.pop(key)
+            del ws
+            if torch.cuda.is_available():
+                torch.cuda.empty_cache()
+        ws = Workspace(device, rows, with_input_grad)
+        _SHARED[key] = ws
+    elif with_input_grad and not ws.with_input_grad:
+        ws.with_input_grad = True
+        if ws.dA is not None:
+            ws.dA[0] = torch.zeros(ws.rows, S2D_PER_SAMPLE, dtype=torch.float32, device=device)
+    return ws
+
+
 def _splits_for(m_tiles: int, n_tiles: int, k_iters: int, cap: int = 8) -> int:
     tiles = max(1, m_tiles * n_tiles)
     s = max(1, min(cap, (2 * 148) // tiles))

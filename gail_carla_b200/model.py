@@ -74,9 +74,7 @@ class PolicyEngine:
             self.dirty = False
 
     def workspace(self, rows: int) -> E.Workspace:
-        dev = self.flat.flat.device
-        if self.ws is None or self.ws.rows < rows or self.ws.device != dev:
-            self.ws = E.Workspace(dev, rows, with_input_grad=False)
+        self.ws = E.shared_workspace(self.flat.flat.device, rows, with_input_grad=False)
         return self.ws
 
     # ---- forward -----------------------------------------------------------------------------------------

@@ -56,9 +56,7 @@ class CriticEngine:
             self.dirty = False
 
     def workspace(self, rows: int) -> E.Workspace:
-        dev = self.flat.flat.device
-        if self.ws is None or self.ws.rows < rows or self.ws.device != dev:
-            self.ws = E.Workspace(dev, rows, with_input_grad=True)
+        self.ws = E.shared_workspace(self.flat.flat.device, rows, with_input_grad=True)
         return self.ws
 
     # rows [row0,row0+B) <- images / metrics / actions given as dense rows or gathered by idx
@@ -198,6 +196,45 @@ class Discriminator(nn.Module):
             eng.update_step(B, alpha, acc, float(lambda_))
             return (float(lambda_) * acc[4] / B).float()
 
+    def _prefetched(self, pairs):
+        """Yield (expert tensors on the device, idx) with the host->device copy of the NEXT expert batch issued on a
+        side stream while the current batch is being processed (the expert loader hands out host tensors,
+        algo/wdgail.py:112,119; at B=4096 a batch is 1.8 GB)."""
+        dev = self._dev()
+        if dev.type != "cuda":
+            for batch, idx in pairs:
+                yield self._to_dev(*batch), idx
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+
+        def stage(pair):
+            batch, idx = pair
+            self._copy_stream.wait_stream(main)       # do not overwrite buffers the main stream may still read
+            with torch.cuda.stream(self._copy_stream):
+                ts = [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in batch]
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return ts, idx, ev
+
+        it = iter(pairs)
+        try:
+            cur = stage(next(it))
+        except StopIteration:
+            return
+        while cur is not None:
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            ts, idx, ev = cur
+            main.wait_event(ev)
+            for t in ts:
+                t.record_stream(main)
+            yield ts, idx
+            cur = nxt
+
     # ---- algo/wdgail.py:100-147
     def update(self, expert_loader, rollouts):
         eng = self.engine
@@ -208,8 +245,7 @@ class Discriminator(nn.Module):
         acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
         with torch.no_grad():
-            for expert_batch, idx in zip(expert_loader, rollouts.minibatch_indices(B)):
-                e_obs, e_met, e_act = self._to_dev(*expert_batch)
+            for (e_obs, e_met, e_act), idx in self._prefetched(zip(expert_loader, rollouts.minibatch_indices(B))):
                 if e_obs.shape[0] != B:
                     raise ValueError("expert batches must all have expert_loader.batch_size rows (drop_last=True)")
                 eng.workspace(3 * B)
