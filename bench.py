@@ -147,7 +147,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-LAUNCHES_PER_CALL = {"gc_conv_dgrad": 4, "gc_welford_merge": 2, "gc_small_linear_bwd": 2}
+LAUNCHES_PER_CALL = {"gc_welford_merge": 2, "gc_small_linear_bwd": 2}
 
 
 class Profiler:
@@ -156,6 +156,7 @@ class Profiler:
 
     def __init__(self, A):
         self.A, self.calls, self.launches, self.records, self.armed = A, 0, 0, [], False
+        self.other = []
         self._orig = A.call
         A.call = self._call
 
@@ -164,12 +165,25 @@ class Profiler:
         self.launches += LAUNCHES_PER_CALL.get(name, 1)
         fl = self._flops(name, args) if self.armed else None
         if fl is None:
-            return self._orig(name, *args)
+            if not self.armed:
+                return self._orig(name, *args)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = self._orig(name, *args)
+            e1.record()
+            self.other.append((name, e0, e1))
+            return r
+        key = name
+        if name.startswith("gc_conv"):
+            g = args[0]._obj
+            key = f"{name}[{g.Cin}->{g.Cout}]"
+        elif name.startswith("gc_linear"):
+            key = f"{name}[{'x'.join(str(v) for v in (args[7:10] if name == 'gc_linear_fwd' else args[8:11] if name == 'gc_linear_dgrad' else args[6:9]))}]"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = self._orig(name, *args)
         e1.record()
-        self.records.append((name, fl, e0, e1))
+        self.records.append((key, fl, e0, e1))
         return r
 
     @staticmethod
@@ -193,6 +207,11 @@ class Profiler:
             f, tt, n = by.get(name, (0.0, 0.0, 0))
             by[name] = (f + fl, tt + t, n + 1)
         tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
+        oth = {}
+        for name, e0, e1 in self.other:
+            t, n = oth.get(name, (0.0, 0))
+            oth[name] = (t + e0.elapsed_time(e1) * 1e-3, n + 1)
+        self.other_summary = {k: {"seconds": v[0], "launches": v[1]} for k, v in sorted(oth.items(), key=lambda kv: -kv[1][0])}
         return by, tot_f, tot_t
 
 
@@ -360,7 +379,8 @@ def run_b200(args):
                            "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce"},
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu,
+                "other_kernels_seconds": prof.other_summary}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -336,9 +336,7 @@ int gc_gae_returns(const float* gail_rewards, const float* value_preds, const fl
   // Launch shape.  Few envs: one CTA covers them all and many time chunks run in parallel (short serial chain).
   // Many envs: wide env groups per CTA (long contiguous row segments), few chunks, enough CTAs for every SM.
   int NB = N >= 32 ? 32 : N, threads = 512, L = 16;
-  if (N >= 128 * gc::kNumSMs) { NB = 128; threads = 256; L = 8; }
-  else if (N >= 64 * gc::kNumSMs) { NB = 64; threads = 256; L = 8; }
-  else if (N >= 32 * 2 * gc::kNumSMs) { NB = 32; threads = 256; L = 8; }
+  if (N >= 32 * 2 * gc::kNumSMs) { NB = 32; threads = 256; L = 8; }  // measured best on B200 (profiles/r01_gae_sweep.txt)
   if (const char* cfg = getenv("GC_GAE_CFG")) {  // tuning override: "NB,threads,L"
     int a = 0, b = 0, c = 0;
     if (sscanf(cfg, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && a <= N && b >= a && b <= 512 && (c == 4 || c == 8 || c == 16)) {

@@ -3,6 +3,7 @@
 // Reference op sites: tools/model.py:131-164 (conv stack), :89-128 (FC body/head), algo/wdgail.py:26-32 (critic trunk),
 // algo/wdgail.py:56-98 (gradient-penalty chains reuse dgrad / fprop-with-mask / wgrad).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -128,7 +129,7 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GC_REQUIRE(p.bn % 16 == 0 && p.bn >= 16 && p.bn <= 256, "%s: tile N %d not a multiple of 16 in [16,256]", what, p.bn);
   GC_REQUIRE(p.bk % 8 == 0 && p.bk >= 8, "%s: bk %d not a multiple of 8", what, p.bk);
   if (!pl.a_mn || !pl.b_mn) GC_REQUIRE(p.bk == 32, "%s: K-major operands need bk == 32 (got %d)", what, p.bk);
-  p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
+  if (p.a_bytes == 0) p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
   const int bpan = (p.bn + 31) / 32;
   p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
   p.b_bytes = (p.b_bytes + 1023) & ~1023;
@@ -257,9 +258,9 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
   p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
   // D (+ mask source with the same geometry)
   const int inner = std::min(32, p.bn);
-  if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD)) return e;
-  if (epilogue == EPI_MASK) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX)) return e; }
-  else p.mapX = p.mapD;
+  if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
+  if (epilogue == EPI_MASK) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
+  else p.mapX[0] = p.mapD[0];
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
   p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
   p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
@@ -268,61 +269,69 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
 }
 
 // dx[b, S*j+py, S*i+px, c] = mask * sum_{a,b',n} dy[b, j-a, i-b', n] * wd[cls][c][a][b'][n],  cls = py*S+px,
-// taps a < KH/S, b' < KW/S.  One launch per parity class.  mask = LeakyReLU'(sign of mask_src at the output position).
+// taps a < KH/S, b' < KW/S.  All S*S parity classes share the same A rows (dy at (j-a, i-b')), so they are ONE GEMM with
+// N = S*S*Cin output columns: dy is fetched once instead of S*S times and the MMA runs at N >= 128 instead of Cin.  Each
+// 32-column output panel belongs to one class and is stored through that class's strided tensor map.
+// mask = LeakyReLU'(sign of mask_src at the output position).
 int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, float* dx, float slope,
                   void* stream) {
   if (int e = check_geom(g, "gc_conv_dgrad")) return e;
   GC_REQUIRE(dy && wd && dx, "gc_conv_dgrad: null pointer");
   GC_REQUIRE(g->KH % g->S == 0 && g->KW % g->S == 0, "gc_conv_dgrad: taps must be a multiple of the stride");
   GC_REQUIRE(g->Cout % 32 == 0 && g->Cin % 16 == 0 && g->Cin <= 256, "gc_conv_dgrad: Cout%%32, Cin%%16, Cin<=256 required");
+  GC_REQUIRE(g->S == 1 || (g->S == 2 && g->Cin % 32 == 0), "gc_conv_dgrad: stride 1, or stride 2 with Cin%%32 == 0");
   const int TA = g->KH / g->S, TB = g->KW / g->S;
   const int Kd = TA * TB * g->Cout;
+  const int ncls = g->S * g->S;
+  const int Ntot = ncls * g->Cin;
+  const int NJ = cdiv(g->H, g->S), NI = cdiv(g->W, g->S);  // class (0,0) has the largest pixel grid
+  Plan pl;
+  GemmParams& p = pl.p;
+  const PixBox bx = choose_box(NI, NJ, g->B, 128, 1, 0.0);
+  p.bn = std::min(256, Ntot);
+  GC_REQUIRE(Ntot % p.bn == 0, "gc_conv_dgrad: S*S*Cin=%d not a multiple of the tile N %d", Ntot, p.bn);
+  p.bk = 32;
+  p.e0 = cdiv(NI, bx.ox);
+  p.e1 = cdiv(NJ, bx.oy);
+  const int e2 = cdiv(g->B, bx.b);
+  p.f0 = Ntot / p.bn;
+  p.g0 = g->Cout / 32;
+  p.g1 = TB;
+  p.k_iters = p.g0 * TB * TA;
+  // A: dy[B][OHp][OWp][Cout] read at (j - a, i - b'); out-of-range taps are zero-filled by TMA
+  if (int e = make_map(out_spec(g, dy, bx, 32, 1, 1), &p.mapA)) return e;
+  p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[1][K1] = -1; p.a.mul[2][M1] = bx.oy; p.a.mul[2][K2] = -1;
+  p.a.mul[3][M2] = bx.b;
+  p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
+  // B: wd viewed as [ncls*Cin][Kd], k = (a*TB + b')*Cout + n
+  {
+    const uint64_t dim[2] = {(uint64_t)Kd, (uint64_t)Ntot};
+    const uint64_t str[2] = {1, (uint64_t)Kd};
+    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    if (int e = make_map(spec(wd, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+  }
+  p.b.mul[0][K0] = 32; p.b.mul[0][K1] = g->Cout; p.b.mul[0][K2] = TB * g->Cout; p.b.mul[1][N0] = p.bn;
+  p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  // D / mask: one strided map per parity class over dx[B][Hp][Wp][Cin]
+  const int inner = std::min(32, g->Cin);
   for (int py = 0; py < g->S; ++py) {
     for (int px = 0; px < g->S; ++px) {
-      const int NJ = cdiv(g->H - py, g->S), NI = cdiv(g->W - px, g->S);
-      Plan pl;
-      GemmParams& p = pl.p;
-      const PixBox bx = choose_box(NI, NJ, g->B, 128, 1, 0.0);
-      p.bn = g->Cin;
-      p.bk = 32;
-      p.e0 = cdiv(NI, bx.ox);
-      p.e1 = cdiv(NJ, bx.oy);
-      const int e2 = cdiv(g->B, bx.b);
-      p.f0 = 1;
-      p.g0 = g->Cout / 32;
-      p.g1 = TB;
-      p.k_iters = p.g0 * TB * TA;
-      // A: dy[B][OHp][OWp][Cout] read at (j - a, i - b'); out-of-range taps are zero-filled by TMA
-      if (int e = make_map(out_spec(g, dy, bx, 32, 1, 1), &p.mapA)) return e;
-      p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[1][K1] = -1; p.a.mul[2][M1] = bx.oy; p.a.mul[2][K2] = -1;
-      p.a.mul[3][M2] = bx.b;
-      p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
-      // B: wd[cls][Cin][Kd], k = (a*TB + b')*Cout + n
-      {
-        const uint64_t dim[3] = {(uint64_t)Kd, (uint64_t)g->Cin, (uint64_t)(g->S * g->S)};
-        const uint64_t str[3] = {1, (uint64_t)Kd, (uint64_t)Kd * g->Cin};
-        const uint32_t box[3] = {32, (uint32_t)p.bn, 1};
-        if (int e = make_map(spec(wd, 3, dim, str, box, 1, 1), &p.mapB)) return e;
-      }
-      p.b.mul[0][K0] = 32; p.b.mul[0][K1] = g->Cout; p.b.mul[0][K2] = TB * g->Cout; p.b.off[2] = py * g->S + px;
-      p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
-      // D / mask: dx[B][Hp][Wp][Cin] restricted to the parity class
-      const int inner = std::min(32, p.bn);
+      const int cls = py * g->S + px;
       const long base = ((long)py * g->Wp + px) * g->Cin;
-      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)NI, (uint64_t)NJ, (uint64_t)g->B};
+      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)cdiv(g->W - px, g->S), (uint64_t)cdiv(g->H - py, g->S), (uint64_t)g->B};
       const uint64_t str[4] = {1, (uint64_t)g->S * g->Cin, (uint64_t)g->S * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
       const uint32_t box[4] = {(uint32_t)inner, (uint32_t)bx.ox, (uint32_t)bx.oy, (uint32_t)bx.b};
-      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, p.bn >= 32), &p.mapD)) return e;
-      if (mask_src) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, p.bn >= 32), &p.mapX)) return e; }
-      else p.mapX = p.mapD;
-      p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
-      p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
-      p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = g->Cin;
-      pl.grid = dim3(p.e0 * p.e1 * e2, 1, 1);
-      if (int e = finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_dgrad")) return e;
+      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapD[cls])) return e;
+      if (mask_src) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapX[cls])) return e; }
+      else p.mapX[cls] = p.mapD[cls];
     }
   }
-  return 0;
+  p.cols_per_map = ncls > 1 ? g->Cin : 0;
+  p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
+  p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
+  p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = Ntot;
+  pl.grid = dim3(p.e0 * p.e1 * e2, p.f0, 1);
+  return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_dgrad");
 }
 
 // K rows (pixels) per k-iteration for wgrad: a multiple of 8 that leaves room for >= 3 pipeline stages
@@ -333,12 +342,25 @@ static int wgrad_max_rows(int bn) {
   return std::max(8, std::min(64, r));
 }
 
+// wgrad tile N: whole (kx,c) rows of as many ky taps as fit in 256 columns (so dy is re-read as rarely as possible)
+static void wgrad_tile_n(const gc_conv_geom* g, int& bn, int& ky_per, int& n_tiles) {
+  const int KC = g->KW * g->Cin;
+  if (KC >= 256) { bn = 256; ky_per = 1; n_tiles = (KC / 256) * g->KH; }
+  else {
+    ky_per = std::min(g->KH, 256 / KC);
+    while (g->KH % ky_per) --ky_per;
+    bn = KC * ky_per;
+    n_tiles = g->KH / ky_per;
+  }
+}
+
 int gc_conv_wgrad_splits(const gc_conv_geom* g) {
   if (check_geom(g, "gc_conv_wgrad_splits")) return -1;
-  const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(std::min(256, g->KW * g->Cin)), 8, 4.0);
+  int bn, ky_per, n_tiles;
+  wgrad_tile_n(g, bn, ky_per, n_tiles);
+  const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(bn), 8, 4.0);
   const int btiles = cdiv(g->B, bx.b);
-  const int bn = std::min(256, g->KW * g->Cin);
-  const int tiles = cdiv(g->Cout, 128) * (g->KW * g->Cin / bn) * g->KH;
+  const int tiles = cdiv(g->Cout, 128) * n_tiles;
   int z = std::max(1, std::min(btiles, (2 * gc::kNumSMs) / std::max(1, tiles)));
   return z;
 }
@@ -353,27 +375,29 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
   GemmParams& p = pl.p;
   pl.a_mn = pl.b_mn = true;
   const int KC = g->KW * g->Cin;
-  p.bn = std::min(256, KC);
+  int ky_per, n_tiles;
+  wgrad_tile_n(g, p.bn, ky_per, n_tiles);
+  GC_REQUIRE(KC % 32 == 0 && (KC >= 256 ? KC % 256 == 0 : true), "gc_conv_wgrad: unsupported KW*Cin=%d", KC);
   const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(p.bn), 8, 4.0);
-  GC_REQUIRE(KC % p.bn == 0, "gc_conv_wgrad: KW*Cin=%d not a multiple of tile N %d", KC, p.bn);
   p.bk = bx.ox * bx.oy * bx.b;
   p.e0 = cdiv(g->Cout, 128);
   p.e1 = 1;
-  p.f0 = KC / p.bn;
+  p.f0 = KC >= 256 ? KC / 256 : 1;   // n-tile -> (n0 = 256-column block inside a ky row, n1 = ky group)
   p.g0 = cdiv(g->OW, bx.ox);
   p.g1 = cdiv(g->OH, bx.oy);
   const int btiles = cdiv(g->B, bx.b);
   const int g2 = cdiv(btiles, splits);
   p.k_iters = p.g0 * p.g1 * g2;
+  const int per_ky = std::min(KC, 256) / 32;  // 32-column panels per ky row inside one tile
   // A: dy MN-major, panels of 32 output channels
   if (int e = make_map(out_spec(g, dy, bx, 32, 1, 2), &p.mapA)) return e;
   p.a.mul[0][M0] = 128; p.a.mul[1][K0] = bx.ox; p.a.mul[2][K1] = bx.oy; p.a.mul[3][K2] = bx.b; p.a.mul[3][Z] = g2 * bx.b;
   p.a.panel[0] = 32;
   p.a_panels = std::min(4, g->Cout / 32); p.a_panel_bytes = p.bk * 128;
-  // B: x windows MN-major, panels of 32 (kx,c) columns
+  // B: x windows MN-major, panels of 32 (kx,c) columns; panels walk (kx,c) first, then ky
   if (int e = make_map(window_spec(g, x, bx, 2), &p.mapB)) return e;
-  p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = bx.ox; p.b.mul[2][N1] = 1; p.b.mul[3][K1] = bx.oy; p.b.mul[4][K2] = bx.b;
-  p.b.mul[4][Z] = g2 * bx.b; p.b.panel[0] = 32;
+  p.b.mul[0][N0] = 256; p.b.mul[1][K0] = bx.ox; p.b.mul[2][N1] = ky_per; p.b.mul[3][K1] = bx.oy; p.b.mul[4][K2] = bx.b;
+  p.b.mul[4][Z] = g2 * bx.b; p.b.panel[0] = 32; p.b.panel2[2] = 1; p.b.period = per_ky;
   p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
   // D: partial[z][Cout][KH][KC]
   {
@@ -381,13 +405,14 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
     const uint64_t str[4] = {1, (uint64_t)KC, (uint64_t)g->KH * KC, (uint64_t)g->Cout * g->KH * KC};
     const int rows = std::min(128, g->Cout);
     const uint32_t box[4] = {32, 1, (uint32_t)rows, 1};
-    if (int e = make_map(spec(dw_partial, 4, dim, str, box, 0, 1), &p.mapD)) return e;
+    if (int e = make_map(spec(dw_partial, 4, dim, str, box, 0, 1), &p.mapD[0])) return e;
     p.d_box_bytes = rows * 128;
   }
-  p.mapX = p.mapD;
-  p.d.mul[0][N0] = p.bn; p.d.mul[1][N1] = 1; p.d.mul[2][M0] = 128; p.d.mul[3][Z] = 1; p.d.panel[0] = 32;
-  p.epilogue = EPI_STORE; p.n_total = KC;
-  pl.grid = dim3(p.e0, p.f0 * g->KH, splits);
+  p.mapX[0] = p.mapD[0];
+  p.d.mul[0][N0] = 256; p.d.mul[1][N1] = ky_per; p.d.mul[2][M0] = 128; p.d.mul[3][Z] = 1;
+  p.d.panel[0] = 32; p.d.panel2[1] = 1; p.d.period = per_ky;
+  p.epilogue = EPI_STORE; p.n_total = KC * g->KH;
+  pl.grid = dim3(p.e0, n_tiles, splits);
   return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_wgrad");
 }
 
@@ -415,6 +440,22 @@ int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const floa
     if (int e = make_map(spec(x, 2, dim, str, box, 1, 1), &p.mapA)) return e;
   }
   p.a.mul[0][K0] = 32; p.a.mul[1][M0] = 128; p.a_panels = 1; p.a_panel_bytes = 16384;
+  if (const char* ex = getenv("GC_EXP")) {
+    // Bring-up experiment (tests/gpu_probe_desc.py): can a K-major SWIZZLE_128B A descriptor start at a row that is
+    // not a multiple of 8 (mode 1), and can its 8-row groups be 9 rows apart (mode 2: SBO = 1152 B)?
+    int mode = 0, r = 0, bo = 0;
+    if (sscanf(ex, "%d,%d,%d", &mode, &r, &bo) == 3) {
+      if (mode == 1) {
+        p.a_panels = 2; p.a.panel[1] = 128; p.a_bytes = 32768; p.exp_a_off = r * 128; p.exp_a_baseoff = bo;
+      } else if (mode == 2) {
+        const uint64_t dim[2] = {(uint64_t)K, (uint64_t)M}, str[2] = {1, (uint64_t)ldx};
+        const uint32_t box[2] = {32, 9};
+        if (int e = make_map(spec(x, 2, dim, str, box, 1, 1), &p.mapA)) return e;
+        p.a_panels = 16; p.a_panel_bytes = 1152; p.a.panel[1] = 9; p.a_bytes = 20480;
+        p.exp_a_off = r * 128; p.exp_a_sbo = 1152; p.exp_a_baseoff = bo;
+      }
+    }
+  }
   {
     const uint64_t dim[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {1, (uint64_t)ldw};
     const uint32_t box[2] = {32, (uint32_t)p.bn};
@@ -425,10 +466,10 @@ int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const floa
     const int inner = std::min(32, p.bn);
     const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)ldy, (uint64_t)ldy * M};
     const uint32_t box[3] = {(uint32_t)inner, 128, 1};
-    if (int e = make_map(spec(y, 3, dim, str, box, 0, p.bn >= 32), &p.mapD)) return e;
+    if (int e = make_map(spec(y, 3, dim, str, box, 0, p.bn >= 32), &p.mapD[0])) return e;
     p.d_box_bytes = inner * 4 * 128;
   }
-  p.mapX = p.mapD;
+  p.mapX[0] = p.mapD[0];
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.mul[2][Z] = 1; p.d.panel[0] = 32;
   p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = N;
   pl.grid = dim3(p.e0, p.f0, splits);
@@ -464,11 +505,11 @@ int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const 
   {
     const uint64_t dim[2] = {(uint64_t)N, (uint64_t)M}, str[2] = {1, (uint64_t)lddx};
     const uint32_t box[2] = {32, 128};
-    if (int e = make_map(spec(dx, 2, dim, str, box, 0, 1), &p.mapD)) return e;
+    if (int e = make_map(spec(dx, 2, dim, str, box, 0, 1), &p.mapD[0])) return e;
     if (mask_src) {
       const uint64_t strm[2] = {1, (uint64_t)ldm};
-      if (int e = make_map(spec(mask_src, 2, dim, strm, box, 0, 1), &p.mapX)) return e;
-    } else p.mapX = p.mapD;
+      if (int e = make_map(spec(mask_src, 2, dim, strm, box, 0, 1), &p.mapX[0])) return e;
+    } else p.mapX[0] = p.mapD[0];
     p.d_box_bytes = 128 * 128;
   }
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.panel[0] = 32;
@@ -509,10 +550,10 @@ int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float*
   {
     const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)lddw, (uint64_t)lddw * M};
     const uint32_t box[3] = {32, 128, 1};
-    if (int e = make_map(spec(dw, 3, dim, str, box, 0, 1), &p.mapD)) return e;
+    if (int e = make_map(spec(dw, 3, dim, str, box, 0, 1), &p.mapD[0])) return e;
     p.d_box_bytes = 128 * 128;
   }
-  p.mapX = p.mapD;
+  p.mapX[0] = p.mapD[0];
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.mul[2][Z] = 1; p.d.panel[0] = 32;
   p.epilogue = EPI_STORE; p.n_total = N;
   pl.grid = dim3(p.e0, p.f0, splits);

@@ -24,13 +24,16 @@ enum Src { M0 = 0, M1, M2, N0, N1, K0, K1, K2, Z };
 struct TmaAddr {
   int off[5];
   int mul[5][kSrc];
-  int panel[5];  // added once per panel (successive TMA boxes of one operand / successive 32-column output panels)
+  int panel[5];   // added once per panel (successive TMA boxes of one operand / successive 32-column output panels)
+  int panel2[5];  // two-level panel walk: panel q sits at (q % period) * panel + (q / period) * panel2
+  int period;     // 0 = single level
 };
 
 enum Epilogue { EPI_STORE = 0, EPI_BIAS_LRELU = 1, EPI_BIAS = 2, EPI_MASK = 3 };
 
 struct alignas(64) GemmParams {
-  CUtensorMap mapA, mapB, mapD, mapX;
+  CUtensorMap mapA, mapB;
+  CUtensorMap mapD[4], mapX[4];  // output / mask-source maps (one per dgrad parity class, else only [0])
   TmaAddr a, b, d;
   int mt, nt, zt;      // tile grid: m-tiles x n-tiles x z (persistent CTAs walk tile = (z*nt + n)*mt + m)
   int e0, e1;          // m-tile index -> (m0, m1, m2) extents
@@ -49,6 +52,8 @@ struct alignas(64) GemmParams {
   int d_row_bytes;     // 128 (swizzled staging) or bn*4 when bn < 32 (unswizzled)
   int d_box_bytes;     // bytes of one output / mask TMA box (rows may be < 128)
   int nbuf;            // staging buffers: 2, or 4 with EPI_MASK
+  int cols_per_map;    // > 0: output column c goes to map c / cols_per_map at channel c % cols_per_map (merged dgrad)
+  int exp_a_off, exp_a_sbo, exp_a_baseoff;  // bring-up experiment hooks for the A descriptor (0 = normal)
   float slope;
   const float* bias;
 };

@@ -102,6 +102,14 @@ __device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc],
   }
 }
 
+// coordinates of panel q of an operand / output whose tile-level coordinates are `base`
+__device__ __forceinline__ void panel_coords(const TmaAddr& t, const int (&base)[5], int q, int (&c)[5]) {
+  const int q1 = t.period > 0 ? q % t.period : q;
+  const int q2 = t.period > 0 ? q / t.period : 0;
+#pragma unroll
+  for (int d = 0; d < 5; ++d) c[d] = base[d] + q1 * t.panel[d] + q2 * t.panel2[d];
+}
+
 // ------------------------------------------------------------------ the kernel
 __device__ __forceinline__ void decode_tile(const GemmParams& p, int tile, int (&src)[kSrc], int& n_tile) {
   const int mt = tile % p.mt;
@@ -194,15 +202,23 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
           coords(p.a, src, K0, K2 + 1, ca);
           coords(p.b, src, K0, K2 + 1, cb);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+          // panels are walked incrementally (no div/mod on the single producer thread's critical path)
           for (int q = 0; q < p.a_panels; ++q) {
             tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, ca);
 #pragma unroll
             for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
           }
+          int q1 = 0;
           for (int q = 0; q < p.b_panels; ++q) {
             tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
+            if (++q1 == p.b.period) {
+              q1 = 0;
 #pragma unroll
-            for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+              for (int d = 0; d < 5; ++d) cb[d] += p.b.panel2[d] - (p.b.period - 1) * p.b.panel[d];
+            } else {
+#pragma unroll
+              for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+            }
           }
         }
       }
@@ -229,7 +245,9 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t ad = umma_desc(sa + (A_MN ? ks * 1024 : ks * 32), a_lbo, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+            uint64_t ad = umma_desc(sa + p.exp_a_off + (A_MN ? ks * 1024 : ks * 32), a_lbo,
+                                    p.exp_a_sbo ? (uint32_t)p.exp_a_sbo : (A_MN ? 512u : 1024u), A_MN ? 1 : 2);
+            ad |= (uint64_t)(p.exp_a_baseoff & 7) << 49;
             const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
             umma_tf32(tacc, ad, bd, idesc, (k | ks) ? 1u : 0u);
           }
@@ -250,16 +268,27 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
     const bool masked = p.epilogue == EPI_MASK;
     const int nbuf = p.nbuf;
     int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (thread 0 only)
+    // output panel q of a tile -> which tensor map and which coordinates
+    auto out_panel = [&](const int (&base)[5], int n_tile, int q, int (&c)[5]) -> int {
+      if (p.cols_per_map > 0) {
+        const int col = n_tile * p.bn + q * 32;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = base[d];
+        c[0] = p.d.off[0] + col % p.cols_per_map;
+        return col / p.cols_per_map;
+      }
+      panel_coords(p.d, base, q, c);
+      return 0;
+    };
     auto prefetch_one = [&]() {
       if (pf_tile >= total_tiles) return;
-      int src[kSrc], nt, cx[5];
+      int src[kSrc], nt, cb_[5], cx[5];
       decode_tile(p, pf_tile, src, nt);
-      tile_coords(p.d, src, cx);
-#pragma unroll
-      for (int d = 0; d < 5; ++d) cx[d] += pf_q * p.d.panel[d];
+      tile_coords(p.d, src, cb_);
+      const int mi = out_panel(cb_, nt, pf_q, cx);
       const int j = pf_count % nbuf;
       mbar_expect_tx(aux0 + 8 * j, (uint32_t)p.d_box_bytes);
-      tma_load_5d(smem_u32(staging + j * 16384), &p.mapX, aux0 + 8 * j, cx);
+      tma_load_5d(smem_u32(staging + j * 16384), &p.mapX[mi], aux0 + 8 * j, cx);
       ++pf_count;
       if (++pf_q == n_panels) { pf_q = 0; pf_tile += gridDim.x; }
     };
@@ -324,11 +353,11 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         fence_async_smem();
         epi_bar_sync();
         if (threadIdx.x == 0) {
-          tma_store_5d(&p.mapD, smem_u32(buf), cd);
+          int cq[5];
+          const int mi = out_panel(cd, n_tile, q, cq);
+          tma_store_5d(&p.mapD[mi], smem_u32(buf), cq);
           tma_commit();
         }
-#pragma unroll
-        for (int d = 0; d < 5; ++d) cd[d] += p.d.panel[d];
       }
     }
     if (threadIdx.x == 0) tma_wait_read<0>();

@@ -1,8 +1,8 @@
 """Drop-in for common/running_mean_std.py.
 
 ``mean`` / ``var`` / ``count`` are float64 like the reference (common/running_mean_std.py:5-8).  ``update`` accepts a
-numpy array (host path, identical arithmetic) or a CUDA tensor; for CUDA tensors of shape-() statistics the batch
-moments and the Chan merge run in one pass on the device (gc_welford_merge) and the state stays in HBM until read.
+numpy array (host path, identical arithmetic) or a 1-D CUDA tensor; for CUDA tensors the batch moments and the Chan
+merge run on the device (gc_welford_merge) and the state stays in HBM until one of the attributes is read.
 """
 from __future__ import annotations
 
@@ -25,17 +25,43 @@ class RunningMeanStd(object):
         self._mean = np.zeros(shape, "float64")
         self._var = np.ones(shape, "float64")
         self._count = epsilon
-        self._dev_state = None      # double[3] on the device while device updates are pending
+        self._dev_state = None      # double[3] = {mean, var, count} on the device while device updates are pending
 
     def _pull(self):
         if self._dev_state is not None:
             m, v, c = self._dev_state.cpu().tolist()
-            self._mean, self._var, self._count = np.float64(m) + np.zeros(()), np.float64(v) + np.zeros(()), c
+            self._mean, self._var, self._count = np.array(m, "float64"), np.array(v, "float64"), c
             self._dev_state = None
 
-    mean = property(lambda s: (s._pull(), s._mean)[1], lambda s, v: (s._pull(), setattr(s, "_mean", v))[0])
-    var = property(lambda s: (s._pull(), s._var)[1], lambda s, v: (s._pull(), setattr(s, "_var", v))[0])
-    count = property(lambda s: (s._pull(), s._count)[1], lambda s, v: (s._pull(), setattr(s, "_count", v))[0])
+    @property
+    def mean(self):
+        self._pull()
+        return self._mean
+
+    @mean.setter
+    def mean(self, value):
+        self._pull()
+        self._mean = value
+
+    @property
+    def var(self):
+        self._pull()
+        return self._var
+
+    @var.setter
+    def var(self, value):
+        self._pull()
+        self._var = value
+
+    @property
+    def count(self):
+        self._pull()
+        return self._count
+
+    @count.setter
+    def count(self, value):
+        self._pull()
+        self._count = value
 
     def update(self, x):
         if isinstance(x, torch.Tensor) and x.is_cuda and self._mean.shape == () and x.dim() == 1:
