@@ -178,7 +178,7 @@ class Profiler:
             g = args[0]._obj
             key = f"{name}[{g.Cin}->{g.Cout}]"
         elif name.startswith("gc_linear"):
-            key = f"{name}[{'x'.join(str(v) for v in (args[7:10] if name == 'gc_linear_fwd' else args[8:11] if name == 'gc_linear_dgrad' else args[6:9]))}]"
+            key = f"{name}[{'x'.join(str(v) for v in (args[7:10] if name == 'gc_linear_fwd' else args[9:12] if name == 'gc_linear_dgrad' else args[6:9]))}]"
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         r = self._orig(name, *args)
@@ -194,7 +194,7 @@ class Profiler:
         if name == "gc_linear_fwd":
             return 2.0 * a[7] * a[8] * a[9]
         if name == "gc_linear_dgrad":
-            return 2.0 * a[8] * a[9] * a[10]
+            return 2.0 * a[9] * a[10] * a[11]
         if name == "gc_linear_wgrad":
             return 2.0 * a[6] * a[7] * a[8]
         return None
@@ -231,7 +231,7 @@ def hbm_microbench(A, dev, pk):
                 ts.append(e0.elapsed_time(e1) * 1e-3)
         return statistics.median(ts)
 
-    for T, N in ((2048, 16), (4096, 16384)):
+    for T, N in ((2048, 16), (4096, 18944)):   # configs[1] size, and an asymptotic size (N = 148 SMs x 4 CTAs x 32 envs)
         r = torch.rand(T, N, 1, device=dev); v = torch.randn(T + 1, N, 1, device=dev); m = torch.ones(T + 1, N, 1, device=dev)
         ret = torch.zeros_like(v)
         t = timeit(lambda: A.gae_returns(r, v, m, ret, 0.99, 0.95))

@@ -53,12 +53,12 @@ _SIGNATURES = {
     "gc_unprep_fc1_wgrad": [_P, _I, _P, _I, _I, _L, _P],
     "gc_grad_sumsq": [_P, _L, _P, _P],
     "gc_clip_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _P],
-    "gc_conv_fprop": [_G, _P, _P, _P, _P, _P, _I, _F, _P],
-    "gc_conv_dgrad": [_G, _P, _P, _P, _P, _F, _P],
+    "gc_conv_fprop": [_G, _P, _P, _P, _P, _P, _P, _I, _F, _P],
+    "gc_conv_dgrad": [_G, _P, _P, _P, _P, _P, _F, _P],
     "gc_conv_wgrad_splits": [_G],
     "gc_conv_wgrad": [_G, _P, _P, _P, _I, _P],
     "gc_linear_fwd": [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
-    "gc_linear_dgrad": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P],
+    "gc_linear_dgrad": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _F, _P],
     "gc_linear_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["gc_last_error_string", "gc_abi_version"])
@@ -235,12 +235,14 @@ def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, b
 
 
 # ------------------------------------------------------------------ tcgen05 contractions
-def conv_fprop(geom: ConvGeom, x, w, bias, y, epilogue, slope=0.2, mask_src=None):
-    call("gc_conv_fprop", C.byref(geom), _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(y), epilogue, slope, _stream())
+def conv_fprop(geom: ConvGeom, x, w, bias, y, epilogue, slope=0.2, mask_src=None, mask_bits=None):
+    call("gc_conv_fprop", C.byref(geom), _ptr(x), _ptr(w), _ptr(bias), _ptr(mask_src), _ptr(mask_bits, torch.int32), _ptr(y),
+         epilogue, slope, _stream())
 
 
-def conv_dgrad(geom: ConvGeom, dy, wd, dx, mask_src=None, slope=0.2):
-    call("gc_conv_dgrad", C.byref(geom), _ptr(dy), _ptr(wd), _ptr(mask_src), _ptr(dx), slope, _stream())
+def conv_dgrad(geom: ConvGeom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None):
+    call("gc_conv_dgrad", C.byref(geom), _ptr(dy), _ptr(wd), _ptr(mask_src), _ptr(mask_bits, torch.int32), _ptr(dx), slope,
+         _stream())
 
 
 def conv_wgrad_splits(geom: ConvGeom) -> int:
@@ -258,8 +260,9 @@ def linear_fwd(x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue, slope=0.2, split
     call("gc_linear_fwd", _ptr(x), ldx, _ptr(w), ldw, _ptr(bias), _ptr(y), ldy, M, N, K, epilogue, slope, splits, _stream())
 
 
-def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2):
-    call("gc_linear_dgrad", _ptr(dy), lddy, _ptr(w), ldw, _ptr(mask_src), ldm, _ptr(dx), lddx, M, N, K, slope, _stream())
+def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None):
+    call("gc_linear_dgrad", _ptr(dy), lddy, _ptr(w), ldw, _ptr(mask_src), _ptr(mask_bits, torch.int32), ldm, _ptr(dx), lddx, M, N, K,
+         slope, _stream())
 
 
 def linear_wgrad(dy, lddy, x, ldx, dw, lddw, M, N, K, splits=1):

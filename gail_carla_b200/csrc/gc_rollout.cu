@@ -45,21 +45,31 @@ __global__ void __launch_bounds__(512) gae_scan_kernel(const float* __restrict__
   if (tid < NB) sIn[tid] = 0.f;
   float s1 = 0.f, s2 = 0.f;
 
+  // register double buffering: the loads of super-chunk k+1 are issued before super-chunk k is folded / combined /
+  // replayed, so HBM requests stay in flight across the two block barriers of every iteration
+  float rn[L], vn[L + 1], mn[L];
+  auto load_chunk = [&](int t_hi_, float (&r_)[L], float (&v_)[L + 1], float (&m_)[L]) {
+    const int t0_ = t_hi_ - (C - c) * L;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const int t = t0_ + i;
+      const bool ok = live && t >= 0;
+      const size_t o = (size_t)(ok ? t : 0) * N + (live ? n : 0);
+      r_[i] = ok ? __ldg(rew + o) : 0.f;
+      v_[i] = ok ? __ldg(val + o) : 0.f;
+      m_[i] = ok ? __ldg(mask + o + N) : 0.f;  // masks[t+1]
+    }
+    v_[L] = (live && t0_ + L >= 0) ? __ldg(val + (size_t)(t0_ + L) * N + n) : 0.f;
+  };
+  load_chunk(T, rn, vn, mn);
+
   for (int t_hi = T; t_hi > 0; t_hi -= C * L) {
     const int t0 = t_hi - (C - c) * L;  // first step of this thread's chunk (may be < 0)
     float r[L], v[L + 1], m[L];
-    if (live) {
 #pragma unroll
-      for (int i = 0; i < L; ++i) {
-        const int t = t0 + i;
-        const bool ok = t >= 0;
-        const size_t o = (size_t)(ok ? t : 0) * N + n;
-        r[i] = ok ? __ldg(rew + o) : 0.f;
-        v[i] = ok ? __ldg(val + o) : 0.f;
-        m[i] = ok ? __ldg(mask + o + N) : 0.f;  // masks[t+1]
-      }
-      v[L] = (t0 + L >= 0) ? __ldg(val + (size_t)(t0 + L) * N + n) : 0.f;
-    }
+    for (int i = 0; i < L; ++i) { r[i] = rn[i]; v[i] = vn[i]; m[i] = mn[i]; }
+    v[L] = vn[L];
+    if (t_hi - C * L > 0) load_chunk(t_hi - C * L, rn, vn, mn);
     float A = 1.f, B = 0.f;
     if (live) {
 #pragma unroll
@@ -336,7 +346,7 @@ int gc_gae_returns(const float* gail_rewards, const float* value_preds, const fl
   // Launch shape.  Few envs: one CTA covers them all and many time chunks run in parallel (short serial chain).
   // Many envs: wide env groups per CTA (long contiguous row segments), few chunks, enough CTAs for every SM.
   int NB = N >= 32 ? 32 : N, threads = 512, L = 16;
-  if (N >= 32 * 2 * gc::kNumSMs) { NB = 32; threads = 256; L = 8; }  // measured best on B200 (profiles/r01_gae_sweep.txt)
+  if (N >= 32 * 2 * gc::kNumSMs) { NB = 32; threads = 256; L = 16; }  // measured best on B200 (profiles/r01_gae_sweep.txt)
   if (const char* cfg = getenv("GC_GAE_CFG")) {  // tuning override: "NB,threads,L"
     int a = 0, b = 0, c = 0;
     if (sscanf(cfg, "%d,%d,%d", &a, &b, &c) == 3 && a > 0 && a <= N && b >= a && b <= 512 && (c == 4 || c == 8 || c == 16)) {

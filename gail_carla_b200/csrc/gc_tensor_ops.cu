@@ -19,24 +19,30 @@ inline int grid_for(long n, int threads, int per_sm) {
 }
 
 // ---- image gather: CHW fp32 storage row -> normalised space-to-depth NHWC tile -----------------------------
-// One CTA per (sample, s2d row Y): stage 3 channels x 2 rows x 192 floats in smem (coalesced reads), then write
-// the 96 x 16 = 1536 output floats of that row contiguously.
+// One CTA per (sample, group of 4 s2d rows): stage 4 x 3 channels x 2 image rows x 192 floats in smem with float4
+// loads (3 independent 16-byte loads in flight per thread), then write the 4 x 96 x 16 output floats contiguously.
+constexpr int kGatherRows = 4;
 __global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
                                                              float* __restrict__ out) {
-  __shared__ float tile[kObsC][2][kObsW + 1];
-  const int b = blockIdx.y, Y = blockIdx.x;
+  __shared__ __align__(16) float tile[kGatherRows][kObsC][2][kObsW + 4];
+  const int b = blockIdx.y, Y0 = blockIdx.x * kGatherRows;
   const long row = idx ? idx[b] : b;
-  const float* s = src + row * (long)(kObsC * kObsH * kObsW);
-  for (int i = threadIdx.x; i < kObsC * 2 * kObsW; i += blockDim.x) {
-    const int x = i % kObsW, dy = (i / kObsW) % 2, c = i / (2 * kObsW);
-    tile[c][dy][x] = (__ldg(s + ((long)c * kObsH + 2 * Y + dy) * kObsW + x) - c_mean[c]) / c_std[c];
+  const float4* s4 = reinterpret_cast<const float4*>(src + row * (long)(kObsC * kObsH * kObsW));
+  constexpr int kRowV = kObsW / 4;  // float4 per image row
+  for (int i = threadIdx.x; i < kGatherRows * kObsC * 2 * kRowV; i += blockDim.x) {
+    const int xv = i % kRowV, dy = (i / kRowV) % 2, c = (i / (2 * kRowV)) % kObsC, yy = i / (2 * kRowV * kObsC);
+    float4 v = __ldg(s4 + ((long)c * kObsH + 2 * (Y0 + yy) + dy) * kRowV + xv);
+    const float m = c_mean[c], sd = c_std[c];
+    *reinterpret_cast<float4*>(&tile[yy][c][dy][4 * xv]) =
+        make_float4((v.x - m) / sd, (v.y - m) / sd, (v.z - m) / sd, (v.w - m) / sd);
   }
   __syncthreads();
-  float4* o = reinterpret_cast<float4*>(out + ((long)b * kS2dH + Y) * (kS2dW * kS2dC));
-  for (int i = threadIdx.x; i < kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,0) of one (X,dy,dx)
-    const int X = i >> 2, dy = (i >> 1) & 1, dx = i & 1;
+  float4* o = reinterpret_cast<float4*>(out + ((long)b * kS2dH + Y0) * (kS2dW * kS2dC));
+  for (int i = threadIdx.x; i < kGatherRows * kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,0) of one (Y,X,dy,dx)
+    const int yy = i / (kS2dW * 4), j = i % (kS2dW * 4);
+    const int X = j >> 2, dy = (j >> 1) & 1, dx = j & 1;
     const int x = 2 * X + dx;
-    o[i] = make_float4(tile[0][dy][x], tile[1][dy][x], tile[2][dy][x], 0.f);
+    o[i] = make_float4(tile[yy][0][dy][x], tile[yy][1][dy][x], tile[yy][2][dy][x], 0.f);
   }
 }
 
@@ -395,7 +401,8 @@ extern "C" {
 int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B, void* stream) {
   GC_REQUIRE(src && out && B > 0, "gc_gather_obs_s2d: bad arguments");
   GC_REQUIRE(B <= 65535, "gc_gather_obs_s2d: B=%d exceeds grid.y", B);
-  gather_obs_s2d_kernel<<<dim3(kS2dH, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
+  GC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_s2d: pointers must be 16-byte aligned");
+  gather_obs_s2d_kernel<<<dim3(kS2dH / kGatherRows, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
   return gc::launch_status("gather_obs_s2d_kernel");
 }
 

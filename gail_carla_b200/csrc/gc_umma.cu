@@ -130,17 +130,27 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GC_REQUIRE(p.bk % 8 == 0 && p.bk >= 8, "%s: bk %d not a multiple of 8", what, p.bk);
   if (!pl.a_mn || !pl.b_mn) GC_REQUIRE(p.bk == 32, "%s: K-major operands need bk == 32 (got %d)", what, p.bk);
   if (p.a_bytes == 0) p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
+  if (p.taps == 0) p.taps = 1;
+  if (p.row_box[0] == 0) { p.row_box[0] = 128; p.row_box[1] = 1; p.row_box[2] = 1; }
   const int bpan = (p.bn + 31) / 32;
-  p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
-  p.b_bytes = (p.b_bytes + 1023) & ~1023;
-  p.nbuf = p.epilogue == EPI_MASK ? 4 : 2;
+  if (p.b_resident) {
+    p.b_bytes = 0;
+    p.b_slab_bytes = p.bn * 128;
+    GC_REQUIRE(!pl.b_mn && pl.grid.y == 1 && p.k_iters * p.taps <= 64, "%s: resident-B mode needs K-major B, one n-tile, <= 64 (k,tap) pairs", what);
+  } else {
+    p.b_slabs = 0; p.b_slab_bytes = 0;
+    p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
+    p.b_bytes = (p.b_bytes + 1023) & ~1023;
+  }
+  const int resident = p.b_slabs * p.b_slab_bytes;
+  p.nbuf = (p.epilogue == EPI_MASK && p.bits_in == nullptr) ? (p.b_resident ? 3 : 4) : 2;
   p.tmem_cols = pow2_cols(2 * bpan * 32);  // two accumulator stages
   p.d_row_bytes = p.bn >= 32 ? 128 : p.bn * 4;
   const int stage = p.a_bytes + p.b_bytes;
-  const int fixed = p.nbuf * 16384 + 2048;
+  const int fixed = p.nbuf * 16384 + 4096 + resident;  // staging + barriers/bias/alignment slack + resident weights
   int stages = (kSmemBudget - fixed) / stage;
   stages = std::min(stages, 8);
-  GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B)", what, stage);
+  GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B, fixed %d B)", what, stage, fixed);
   p.stages = stages;
   p.mt = pl.grid.x; p.nt = pl.grid.y; p.zt = pl.grid.z;
   const long total_tiles = (long)p.mt * p.nt * p.zt;
@@ -225,12 +235,112 @@ extern "C" {
 
 // y[b,oy,ox,n] = epi( sum_{ky,kx,c} x[b, S*oy+ky, S*ox+kx, c] * w[n][ky][kx][c] )
 int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const float* bias, const float* mask_src,
-                  float* y, int epilogue, float slope, void* stream) {
+                  unsigned* mask_bits, float* y, int epilogue, float slope, void* stream) {
   if (int e = check_geom(g, "gc_conv_fprop")) return e;
   GC_REQUIRE(x && w && y, "gc_conv_fprop: null pointer");
   GC_REQUIRE(epilogue >= 0 && epilogue <= 3, "gc_conv_fprop: bad epilogue %d", epilogue);
   if (epilogue == EPI_BIAS_LRELU || epilogue == EPI_BIAS) GC_REQUIRE(bias, "gc_conv_fprop: bias epilogue without bias");
-  if (epilogue == EPI_MASK) GC_REQUIRE(mask_src, "gc_conv_fprop: mask epilogue without mask source");
+  if (epilogue == EPI_MASK) GC_REQUIRE(mask_src || mask_bits, "gc_conv_fprop: mask epilogue without mask source");
+  // bit mask of the output tensor y: written by the bias+LeakyReLU epilogue, read by the mask epilogue
+  auto set_bits = [&](GemmParams& p, const PixBox& bx) {
+    if (!mask_bits) return;
+    if (epilogue == EPI_BIAS_LRELU) p.bits_out = mask_bits;
+    else if (epilogue == EPI_MASK) p.bits_in = mask_bits;
+    p.row_box[0] = bx.ox; p.row_box[1] = bx.oy; p.row_box[2] = bx.b;
+    p.row_ext[0][0] = g->OW; p.row_ext[0][1] = g->OH; p.row_ext[0][2] = g->B;
+    p.bit_str[0] = g->Cout; p.bit_str[1] = (long)g->OWp * g->Cout; p.bit_str[2] = g->out_batch_stride;
+    p.bit_base[0] = 0;
+  };
+  if (mask_bits) GC_REQUIRE(g->Cout % 32 == 0 && g->out_batch_stride % 32 == 0, "gc_conv_fprop: bit masks need Cout and batch stride multiples of 32");
+  // Small-channel stride-2 layers (conv2): "patch mode".  The weight matrix (<= 128 KB) is loaded once per CTA and stays in
+  // shared memory; for each of the 4 input parity classes (py,px) ONE (8+1)x(16+1)-pixel patch of the class sub-image is
+  // TMA-loaded and serves the class's 4 taps (a,b) as shifted A views (descriptor start (a*9+b)*128 B, 8-row groups
+  // 9 rows = 1152 B apart - see profiles/r01_umma_descriptor_experiment.txt).  L2->SM traffic per 128-pixel tile drops
+  // from 16 x 16 KB (A) + 128 KB (B) to 4 x 19 KB.
+  if (g->S == 2 && g->KH == 4 && g->KW == 4 && g->Cin % 32 == 0 && (long)g->Cout * g->Cin * 64 <= 131072 && g->Wp % 2 == 0 &&
+      g->Hp % 2 == 0 && g->Cout <= 256 && getenv("GC_NO_PATCH") == nullptr) {
+    Plan pl;
+    GemmParams& p = pl.p;
+    const int C = g->Cin, nchunk = C / 32;
+    const PixBox bx{8, 16, 1};
+    p.bn = g->Cout;
+    p.bk = 32;
+    p.e0 = cdiv(g->OW, 8); p.e1 = cdiv(g->OH, 16);
+    p.g0 = nchunk; p.g1 = 2;                      // k -> (chunk, px, py)
+    p.k_iters = 4 * nchunk;
+    {
+      const uint64_t dim[5] = {(uint64_t)2 * C, (uint64_t)g->Wp / 2, 2, (uint64_t)g->Hp / 2, (uint64_t)g->B};
+      const uint64_t str[5] = {1, (uint64_t)2 * C, (uint64_t)g->Wp * C, (uint64_t)2 * g->Wp * C, (uint64_t)g->in_batch_stride};
+      const uint32_t box[5] = {32, 9, 1, 17, 1};
+      if (int e = make_map(spec(x, 5, dim, str, box, 1, 1), &p.mapA)) return e;
+    }
+    p.a.mul[0][K0] = 32; p.a.mul[0][K1] = C; p.a.mul[2][K2] = 1; p.a.mul[1][M0] = 8; p.a.mul[3][M1] = 16; p.a.mul[4][M2] = 1;
+    p.a_panels = 1; p.a_panel_bytes = 9 * 17 * 128; p.a_bytes = 20480;
+    p.exp_a_sbo = 9 * 128;
+    p.taps = 4;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) p.tap_off[a * 2 + b] = (a * 9 + b) * 128;
+    for (int k = 0; k < p.k_iters; ++k) {
+      const int chunk = k % nchunk, px = (k / nchunk) % 2, py = k / (2 * nchunk);
+      for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b)
+        p.b_tab[k * 4 + a * 2 + b] = (unsigned char)((((2 * a + py) * 4 + (2 * b + px)) * nchunk) + chunk);
+    }
+    {
+      const int K = 16 * C;
+      const uint64_t dim[2] = {(uint64_t)K, (uint64_t)g->Cout}, str[2] = {1, (uint64_t)K};
+      const uint32_t box[2] = {32, (uint32_t)p.bn};
+      if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+    }
+    p.b_resident = 1; p.b_slabs = 16 * nchunk;
+    const int inner = std::min(32, p.bn);
+    if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
+    p.mapX[0] = p.mapD[0];
+    p.d.mul[1][M0] = 8; p.d.mul[2][M1] = 16; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
+    p.d_box_bytes = inner * 4 * 128;
+    p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
+    set_bits(p, bx);
+    if (p.bits_in == nullptr && epilogue == EPI_MASK) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
+    pl.grid = dim3(p.e0 * p.e1 * g->B, 1, 1);
+    return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_fprop(patch)");
+  }
+  // conv1 in its space-to-depth form (2x2 taps, stride 1, 16 channels): "row-patch mode".  A window row (2 pixels x 16
+  // channels) is exactly one 128-byte K slab, so the two vertical taps of a 32x4-pixel tile are two views, 32 rows apart,
+  // of ONE 32x5-row patch; the 8 KB weight matrix stays resident in shared memory.  TMA row requests per tile drop from
+  // 256 (A) + 64 (B) to 160.
+  if (g->S == 1 && g->KH == 2 && g->KW == 2 && g->Cin == 16 && g->Cout <= 256 && g->OW >= 32 && getenv("GC_NO_PATCH") == nullptr) {
+    Plan pl;
+    GemmParams& p = pl.p;
+    const PixBox bx{32, 4, 1};
+    p.bn = g->Cout;
+    p.bk = 32;
+    p.e0 = cdiv(g->OW, 32); p.e1 = cdiv(g->OH, 4);
+    p.k_iters = 1;
+    {
+      const uint64_t dim[4] = {32, (uint64_t)g->OW, (uint64_t)g->H, (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)g->Cin, (uint64_t)g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
+      const uint32_t box[4] = {32, 32, 5, 1};
+      if (int e = make_map(spec(x, 4, dim, str, box, 1, 1), &p.mapA)) return e;
+    }
+    p.a.mul[1][M0] = 32; p.a.mul[2][M1] = 4; p.a.mul[3][M2] = 1;
+    p.a_panels = 1; p.a_panel_bytes = 32 * 5 * 128; p.a_bytes = 20480;
+    p.taps = 2; p.tap_off[0] = 0; p.tap_off[1] = 32 * 128;
+    p.b_tab[0] = 0; p.b_tab[1] = 1;
+    {
+      const uint64_t dim[2] = {64, (uint64_t)g->Cout}, str[2] = {1, 64};
+      const uint32_t box[2] = {32, (uint32_t)p.bn};
+      if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+    }
+    p.b_resident = 1; p.b_slabs = 2;
+    const int inner = std::min(32, p.bn);
+    if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
+    if (epilogue == EPI_MASK && !mask_bits) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
+    else p.mapX[0] = p.mapD[0];
+    p.d.mul[1][M0] = 32; p.d.mul[2][M1] = 4; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
+    p.d_box_bytes = inner * 4 * 128;
+    p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
+    set_bits(p, bx);
+    pl.grid = dim3(p.e0 * p.e1 * g->B, 1, 1);
+    return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_fprop(row-patch)");
+  }
   Plan pl;
   GemmParams& p = pl.p;
   const PixBox bx = choose_box(g->OW, g->OH, g->B, 128, 1, 0.0);
@@ -259,11 +369,12 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
   // D (+ mask source with the same geometry)
   const int inner = std::min(32, p.bn);
   if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
-  if (epilogue == EPI_MASK) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
+  if (epilogue == EPI_MASK && !mask_bits) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
   else p.mapX[0] = p.mapD[0];
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
   p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
   p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
+  set_bits(p, bx);
   pl.grid = dim3(p.e0 * p.e1 * e2, p.f0, 1);
   return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_fprop");
 }
@@ -273,8 +384,8 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
 // N = S*S*Cin output columns: dy is fetched once instead of S*S times and the MMA runs at N >= 128 instead of Cin.  Each
 // 32-column output panel belongs to one class and is stored through that class's strided tensor map.
 // mask = LeakyReLU'(sign of mask_src at the output position).
-int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, float* dx, float slope,
-                  void* stream) {
+int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, const unsigned* mask_bits,
+                  float* dx, float slope, void* stream) {
   if (int e = check_geom(g, "gc_conv_dgrad")) return e;
   GC_REQUIRE(dy && wd && dx, "gc_conv_dgrad: null pointer");
   GC_REQUIRE(g->KH % g->S == 0 && g->KW % g->S == 0, "gc_conv_dgrad: taps must be a multiple of the stride");
@@ -285,6 +396,71 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
   const int ncls = g->S * g->S;
   const int Ntot = ncls * g->Cin;
   const int NJ = cdiv(g->H, g->S), NI = cdiv(g->W, g->S);  // class (0,0) has the largest pixel grid
+  if (mask_bits) GC_REQUIRE(g->Cin % 32 == 0 && g->in_batch_stride % 32 == 0, "gc_conv_dgrad: bit masks need Cin and batch stride multiples of 32");
+  const bool want_mask = mask_src != nullptr || mask_bits != nullptr;
+  // bit mask of the activation tensor that dx has the geometry of (one strided class view per output map)
+  auto set_bits = [&](GemmParams& p, int box_i, int box_j, int box_b) {
+    if (!mask_bits) return;
+    p.bits_in = mask_bits;
+    p.row_box[0] = box_i; p.row_box[1] = box_j; p.row_box[2] = box_b;
+    for (int py = 0; py < g->S; ++py) for (int px = 0; px < g->S; ++px) {
+      const int cls = py * g->S + px;
+      p.row_ext[cls][0] = cdiv(g->W - px, g->S); p.row_ext[cls][1] = cdiv(g->H - py, g->S); p.row_ext[cls][2] = g->B;
+      p.bit_base[cls] = ((long)py * g->Wp + px) * g->Cin;
+    }
+    p.bit_str[0] = (long)g->S * g->Cin; p.bit_str[1] = (long)g->S * g->Wp * g->Cin; p.bit_str[2] = g->in_batch_stride;
+  };
+  // Patch mode for the small layer (conv2): resident weights (all classes, <= 128 KB) and one (8+1)x(16+1) patch of dy per
+  // 32-channel chunk serving the 4 taps (a,b') as shifted A views.
+  if (g->S == 2 && TA == 2 && TB == 2 && (long)Ntot * Kd * 4 <= 131072 && Ntot <= 256 && getenv("GC_NO_PATCH") == nullptr) {
+    Plan pl;
+    GemmParams& p = pl.p;
+    const int nchunk = g->Cout / 32;
+    p.bn = Ntot;
+    p.bk = 32;
+    p.e0 = cdiv(NI, 8); p.e1 = cdiv(NJ, 16);
+    p.g0 = nchunk; p.g1 = 1;
+    p.k_iters = nchunk;
+    {
+      const uint64_t dim[4] = {(uint64_t)g->Cout, (uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)g->Cout, (uint64_t)g->OWp * g->Cout, (uint64_t)g->out_batch_stride};
+      const uint32_t box[4] = {32, 9, 17, 1};
+      if (int e = make_map(spec(dy, 4, dim, str, box, 1, 1), &p.mapA)) return e;
+    }
+    p.a.mul[0][K0] = 32; p.a.mul[1][M0] = 8; p.a.off[1] = -1; p.a.mul[2][M1] = 16; p.a.off[2] = -1; p.a.mul[3][M2] = 1;
+    p.a_panels = 1; p.a_panel_bytes = 9 * 17 * 128; p.a_bytes = 20480;
+    p.exp_a_sbo = 9 * 128;
+    p.taps = 4;
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) {
+      p.tap_off[a * 2 + b] = ((1 - a) * 9 + (1 - b)) * 128;   // dy[j-a, i-b'] inside the patch whose origin is (j0-1, i0-1)
+      for (int k = 0; k < nchunk; ++k) p.b_tab[k * 4 + a * 2 + b] = (unsigned char)((a * 2 + b) * nchunk + k);
+    }
+    {
+      const uint64_t dim[2] = {(uint64_t)Kd, (uint64_t)Ntot}, str[2] = {1, (uint64_t)Kd};
+      const uint32_t box[2] = {32, (uint32_t)p.bn};
+      if (int e = make_map(spec(wd, 2, dim, str, box, 1, 1), &p.mapB)) return e;
+    }
+    p.b_resident = 1; p.b_slabs = 4 * nchunk;
+    const PixBox bx{8, 16, 1};
+    const int inner = std::min(32, g->Cin);
+    for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
+      const int cls = py * 2 + px;
+      const long base = ((long)py * g->Wp + px) * g->Cin;
+      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)cdiv(g->W - px, 2), (uint64_t)cdiv(g->H - py, 2), (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)2 * g->Cin, (uint64_t)2 * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
+      const uint32_t box[4] = {(uint32_t)inner, 8, 16, 1};
+      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, 1), &p.mapD[cls])) return e;
+      if (mask_src && !mask_bits) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, 1), &p.mapX[cls])) return e; }
+      else p.mapX[cls] = p.mapD[cls];
+    }
+    p.cols_per_map = g->Cin;
+    p.d.mul[1][M0] = 8; p.d.mul[2][M1] = 16; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
+    p.d_box_bytes = inner * 4 * 128;
+    p.epilogue = want_mask ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = Ntot;
+    set_bits(p, 8, 16, 1);
+    pl.grid = dim3(p.e0 * p.e1 * g->B, 1, 1);
+    return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_dgrad(patch)");
+  }
   Plan pl;
   GemmParams& p = pl.p;
   const PixBox bx = choose_box(NI, NJ, g->B, 128, 1, 0.0);
@@ -322,14 +498,15 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
       const uint64_t str[4] = {1, (uint64_t)g->S * g->Cin, (uint64_t)g->S * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
       const uint32_t box[4] = {(uint32_t)inner, (uint32_t)bx.ox, (uint32_t)bx.oy, (uint32_t)bx.b};
       if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapD[cls])) return e;
-      if (mask_src) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapX[cls])) return e; }
+      if (mask_src && !mask_bits) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapX[cls])) return e; }
       else p.mapX[cls] = p.mapD[cls];
     }
   }
   p.cols_per_map = ncls > 1 ? g->Cin : 0;
   p.d.mul[1][M0] = bx.ox; p.d.mul[2][M1] = bx.oy; p.d.mul[3][M2] = bx.b; p.d.panel[0] = 32;
   p.d_box_bytes = inner * 4 * bx.ox * bx.oy * bx.b;
-  p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = Ntot;
+  p.epilogue = want_mask ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = Ntot;
+  set_bits(p, bx.ox, bx.oy, bx.b);
   pl.grid = dim3(p.e0 * p.e1 * e2, p.f0, 1);
   return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_dgrad");
 }
@@ -477,8 +654,8 @@ int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const floa
 }
 
 // dx[m][n] = mask * sum_k dy[m][k] * w[k][n]   (w is the forward weight [out=K][in=N], read MN-major - no transpose)
-int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, long ldm, float* dx,
-                    long lddx, int M, int N, int K, float slope, void* stream) {
+int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, const unsigned* mask_bits,
+                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, void* stream) {
   GC_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, "gc_linear_dgrad: bad arguments");
   GC_REQUIRE(lddy % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 && ldm % 4 == 0, "gc_linear_dgrad: pitches must be multiples of 4");
   Plan pl;
@@ -506,14 +683,21 @@ int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const 
     const uint64_t dim[2] = {(uint64_t)N, (uint64_t)M}, str[2] = {1, (uint64_t)lddx};
     const uint32_t box[2] = {32, 128};
     if (int e = make_map(spec(dx, 2, dim, str, box, 0, 1), &p.mapD[0])) return e;
-    if (mask_src) {
+    if (mask_src && !mask_bits) {
       const uint64_t strm[2] = {1, (uint64_t)ldm};
       if (int e = make_map(spec(mask_src, 2, dim, strm, box, 0, 1), &p.mapX[0])) return e;
     } else p.mapX[0] = p.mapD[0];
     p.d_box_bytes = 128 * 128;
   }
   p.d.mul[0][N0] = p.bn; p.d.mul[1][M0] = 128; p.d.panel[0] = 32;
-  p.epilogue = mask_src ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = N;
+  p.epilogue = (mask_src || mask_bits) ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = N;
+  if (mask_bits) {
+    GC_REQUIRE(ldm % 32 == 0, "gc_linear_dgrad: bit masks need a row pitch that is a multiple of 32");
+    p.bits_in = mask_bits;
+    p.row_box[0] = 128; p.row_box[1] = 1; p.row_box[2] = 1;
+    p.row_ext[0][0] = M; p.row_ext[0][1] = 1; p.row_ext[0][2] = 1;
+    p.bit_str[0] = ldm; p.bit_str[1] = 0; p.bit_str[2] = 0; p.bit_base[0] = 0;
+  }
   pl.grid = dim3(p.e0, p.f0, 1);
   return finish_and_launch(pl, (cudaStream_t)stream, "gc_linear_dgrad");
 }

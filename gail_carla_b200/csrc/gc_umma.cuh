@@ -54,6 +54,23 @@ struct alignas(64) GemmParams {
   int nbuf;            // staging buffers: 2, or 4 with EPI_MASK
   int cols_per_map;    // > 0: output column c goes to map c / cols_per_map at channel c % cols_per_map (merged dgrad)
   int exp_a_off, exp_a_sbo, exp_a_baseoff;  // bring-up experiment hooks for the A descriptor (0 = normal)
+  // patch mode: one TMA-loaded input patch per stage serves `taps` shifted A views (convolution taps); B (the whole
+  // weight matrix) is loaded once per CTA and stays resident in shared memory.
+  int taps;             // MMA groups per stage (1 = plain GEMM)
+  int tap_off[4];       // byte offset of each tap's A view inside the stage
+  int b_resident;       // 1: B slabs are loaded once per CTA
+  int b_slabs;          // resident 32-wide K slabs
+  int b_slab_bytes;     // bn * 128
+  unsigned char b_tab[64];  // resident slab used by (k-iteration, tap): b_tab[k * taps + t]
+  // LeakyReLU' bitmask (1 bit per fp32 element of an activation tensor, same linear order): written by the
+  // bias+LeakyReLU epilogue, read by EPI_MASK instead of TMA-loading the fp32 activation tile.
+  unsigned* bits_out;        // nullable
+  const unsigned* bits_in;   // nullable; with EPI_MASK replaces mapX
+  int row_box[3];            // output tile row r -> (r % row_box[0], (r / row_box[0]) % row_box[1], r / (row_box[0]*row_box[1]));
+                             // rows with the third coordinate >= row_box[2] are not part of the tile
+  int row_ext[4][3];         // valid extents of the three row coordinates, per output map
+  long bit_str[3];           // element strides of the three row coordinates in the tensor the bits describe
+  long bit_base[4];          // element offset of each output map's origin in that tensor
   float slope;
   const float* bias;
 };

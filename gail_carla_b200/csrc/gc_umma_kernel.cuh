@@ -93,6 +93,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+__device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 __device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc], int lo, int hi, int (&c)[5]) {
 #pragma unroll
   for (int d = 0; d < 5; ++d) {
@@ -142,14 +144,16 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = p.a_bytes + p.b_bytes;
-  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;  // nbuf x 16 KB, 1024-aligned
+  uint8_t* bres = smem + (size_t)p.stages * stage_bytes;       // resident B slabs (patch mode), 1024-aligned
+  uint8_t* staging = bres + (size_t)p.b_slabs * p.b_slab_bytes;  // nbuf x 16 KB, 1024-aligned
   uint64_t* bars = (uint64_t*)(staging + (size_t)p.nbuf * 16384);
-  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], aux[4]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 8);
+  // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], aux[4], bres
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 9);
+  float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // nt*bn floats (<= 512) for bias epilogues
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
-  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16, aux0 = tempty0 + 16;
+  const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16, aux0 = tempty0 + 16, bres_bar = aux0 + 32;
   const int total_tiles = p.mt * p.nt * p.zt;
   const int acc_cols = ((p.bn + 31) >> 5) << 5;
 
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
     }
     for (int q = 0; q < 4; ++q) mbar_init(aux0 + 8 * q, 1);
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
@@ -172,6 +177,9 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if ((p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) && p.nt * p.bn <= 512) {
+    for (int i = threadIdx.x; i < p.nt * p.bn; i += blockDim.x) s_bias[i] = i < p.n_total ? __ldg(p.bias + i) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -179,7 +187,14 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
 
   if (warp == 4) {
     if (lane == 0) {
-      const uint32_t tx = p.a_panels * p.a_panel_bytes + p.b_panels * p.b_panel_bytes;
+      const uint32_t tx = p.a_panels * p.a_panel_bytes + (p.b_resident ? 0 : p.b_panels * p.b_panel_bytes);
+      if (p.b_resident) {  // the whole weight matrix, once per CTA
+        mbar_expect_tx(bres_bar, (uint32_t)(p.b_slabs * p.b_slab_bytes));
+        for (int s = 0; s < p.b_slabs; ++s) {
+          const int cw[5] = {32 * s, 0, 0, 0, 0};
+          tma_load_5d(smem_u32(bres) + s * p.b_slab_bytes, &p.mapB, bres_bar, cw);
+        }
+      }
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int src[kSrc], n_tile, baseA[5], baseB[5];
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
             for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
           }
           int q1 = 0;
-          for (int q = 0; q < p.b_panels; ++q) {
+          for (int q = 0; q < (p.b_resident ? 0 : p.b_panels); ++q) {
             tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
             if (++q1 == p.b.period) {
               q1 = 0;
@@ -233,6 +248,23 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
       const uint32_t b_lbo = B_MN ? (uint32_t)p.b_panel_bytes : 0u;
       int it = 0, ti = 0;
+      const uint32_t a_sbo = p.exp_a_sbo ? (uint32_t)p.exp_a_sbo : (A_MN ? 512u : 1024u);
+      // constant descriptor halves (see umma_desc): lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version | base_offset | layout
+      const uint64_t a_proto = umma_desc(0, a_lbo, a_sbo, A_MN ? 1 : 2) | ((uint64_t)(p.exp_a_baseoff & 7) << 49);
+      const uint64_t b_proto = umma_desc(0, b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
+      const uint32_t a_lo_base = (uint32_t)a_proto, a_hi = (uint32_t)(a_proto >> 32);
+      const uint32_t b_lo_base = (uint32_t)b_proto, b_hi = (uint32_t)(b_proto >> 32);
+      const uint32_t a_step = A_MN ? 64u : 2u, b_step = B_MN ? 64u : 2u;  // per K-step: 1024 B or 32 B, in 16-byte units
+      const int n_taps = p.taps;
+      const bool b_res = p.b_resident != 0;
+      const uint32_t bres_u32 = smem_u32(bres), b_slab = (uint32_t)p.b_slab_bytes, a_off0 = (uint32_t)p.exp_a_off;
+      int tap_off[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) tap_off[t] = p.tap_off[t];
+      if (p.b_resident) {
+        mbar_wait(bres_bar, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int acc = ti & 1;
         mbar_wait(tempty0 + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
@@ -244,12 +276,21 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            uint64_t ad = umma_desc(sa + p.exp_a_off + (A_MN ? ks * 1024 : ks * 32), a_lbo,
-                                    p.exp_a_sbo ? (uint32_t)p.exp_a_sbo : (A_MN ? 512u : 1024u), A_MN ? 1 : 2);
-            ad |= (uint64_t)(p.exp_a_baseoff & 7) << 49;
-            const uint64_t bd = umma_desc(sb + (B_MN ? ks * 1024 : ks * 32), b_lbo, B_MN ? 512 : 1024, B_MN ? 1 : 2);
-            umma_tf32(tacc, ad, bd, idesc, (k | ks) ? 1u : 0u);
+          // Descriptors differ only in their 14-bit start-address field, so the loop adds to precomputed 32-bit
+          // halves; the 4 K-steps of a 128-byte K-major slab are unrolled (the MMA of a 128xN tile with small N takes
+          // only N/2 cycles, so the single issuing thread must not spend more than that per instruction).
+          for (int t = 0; t < n_taps; ++t) {
+            const uint32_t alo = a_lo_base + ((sa + a_off0 + (uint32_t)tap_off[t]) >> 4);
+            const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[k * n_taps + t] * b_slab : sb) >> 4);
+            if (ksteps == 4) {
+              umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
+              umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
+              umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
+              umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
+            } else {
+              for (int ks = 0; ks < ksteps; ++ks)
+                umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | t | ks) ? 1u : 0u);
+            }
           }
           umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
         }
@@ -265,8 +306,10 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
     const int row = warp * 32 + lane;
     const int n_panels = (p.bn + 31) >> 5;
     const bool swz = p.d_row_bytes == 128;
-    const bool masked = p.epilogue == EPI_MASK;
+    const bool masked = p.epilogue == EPI_MASK && p.bits_in == nullptr;  // TMA-loaded mask tiles
+    const bool bitmask = p.epilogue == EPI_MASK && p.bits_in != nullptr;
     const int nbuf = p.nbuf;
+    const int r0 = row % p.row_box[0], r1 = (row / p.row_box[0]) % p.row_box[1], r2 = row / (p.row_box[0] * p.row_box[1]);
     int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (thread 0 only)
     // output panel q of a tile -> which tensor map and which coordinates
     auto out_panel = [&](const int (&base)[5], int n_tile, int q, int (&c)[5]) -> int {
@@ -292,13 +335,34 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       ++pf_count;
       if (++pf_q == n_panels) { pf_q = 0; pf_tile += gridDim.x; }
     };
-    if (masked && threadIdx.x == 0) { prefetch_one(); prefetch_one(); }
+    if (masked && threadIdx.x == 0) {
+      for (int i = 0; i < nbuf - 2; ++i) prefetch_one();  // mask prefetch distance = nbuf - 2 panels
+    }
     int pc = 0, ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       int src[kSrc], n_tile, cd[5];
       decode_tile(p, tile, src, n_tile);
       tile_coords(p.d, src, cd);
       const int acc = ti & 1;
+      // element offset (in the tensor the bitmask describes) of this thread's row in panel q, or -1 if the row is clipped
+      auto bit_word = [&](int q) -> long {
+        int cq[5];
+        const int mi = out_panel(cd, n_tile, q, cq);
+        const int c1 = cq[1] + r0, c2 = cq[2] + r1, c3 = cq[3] + r2;
+        if (r2 >= p.row_box[2] || c1 >= p.row_ext[mi][0] || c2 >= p.row_ext[mi][1] || c3 >= p.row_ext[mi][2]) return -1;
+        return (p.bit_base[mi] + c1 * p.bit_str[0] + c2 * p.bit_str[1] + c3 * p.bit_str[2] + cq[0]) >> 5;
+      };
+      unsigned mbits[8];
+      if (bitmask) {  // issued before waiting for the accumulator: the loads overlap the tile's mainloop
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          mbits[q] = 0u;
+          if (q < n_panels) {
+            const long wi = bit_word(q);
+            if (wi >= 0) mbits[q] = __ldg(p.bits_in + wi);
+          }
+        }
+      }
       mbar_wait(tfull0 + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_cols);
@@ -306,7 +370,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         uint8_t* buf = staging + (pc % nbuf) * 16384;
         if (threadIdx.x == 0) {
           if (pc >= 2) tma_wait_read<1>();  // the store of panel pc-2 has drained its staging buffer
-          if (masked) prefetch_one();       // panel pc+2 -> buffer (pc+2)%4, free since the wait above
+          if (masked) prefetch_one();       // panel pc+nbuf-2 -> the buffer the store of panel pc-2 just released
         }
         epi_bar_sync();
         float v[32];
@@ -318,12 +382,35 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         }
         const int col0 = n_tile * p.bn + q * 32;
         if (p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) {
+          if (p.nt * p.bn <= 512) {  // bias staged in shared memory: 8 broadcast LDS.128 instead of 32 global loads
+            const float4* sb4 = reinterpret_cast<const float4*>(s_bias + col0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float b = (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
-            const float x = v[j] + b;
-            v[j] = (p.epilogue == EPI_BIAS_LRELU) ? gc::leaky(x, p.slope) : x;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = sb4[j];
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
           }
+          if (p.epilogue == EPI_BIAS_LRELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gc::leaky(v[j], p.slope);
+          }
+        }
+        if (p.bits_out != nullptr && p.epilogue == EPI_BIAS_LRELU) {
+          unsigned w = 0u;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f && col0 + j < p.n_total) ? (1u << j) : 0u;
+          const long wi = bit_word(q);
+          if (wi >= 0) p.bits_out[wi] = w;
+        }
+        if (bitmask) {
+          unsigned w = 0u;
+#pragma unroll
+          for (int qq = 0; qq < 8; ++qq) w = (qq == q) ? mbits[qq] : w;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? 1.f : p.slope;
         }
         const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
         const int nchunk = p.d_row_bytes >> 4;

@@ -106,6 +106,9 @@ class Workspace:
         self.X0 = z(rows, S2D_PER_SAMPLE)
         self.A = [self.X0, z(rows, ACT_ELEMS[1]), z(rows, ACT_ELEMS[2]), z(rows, ACT_ELEMS[3])]
         self.F = z(rows, LDF)
+        # LeakyReLU' bit masks of A1, A2, A3 and F (1 bit per fp32 element, written by the conv fprop epilogues)
+        zi = lambda n: torch.zeros(rows, n, dtype=torch.int32, device=device)
+        self.mbits = [None, zi(ACT_ELEMS[1] // 32), zi(ACT_ELEMS[2] // 32), zi(ACT_ELEMS[3] // 32), zi(LDF // 32)]
         self.dA: Optional[List[torch.Tensor]] = None
         self.with_input_grad = with_input_grad
         self.part: Dict[str, torch.Tensor] = {}
@@ -194,12 +197,19 @@ class ConvStack:
         for i in range(1, 5):
             A.prep_conv_weight(self.flat.p(self.wname(i)), self.wf[i - 1], self.wd[i - 1], CONV_CH[i], CONV_CH[i - 1], i == 1)
 
-    def forward(self, ws: Workspace, B: int, row0: int = 0) -> None:
+    @staticmethod
+    def bits(ws: Workspace, i: int, row0: int):
+        """LeakyReLU' bit mask of activation i.  A1 has none: conv1's forward is epilogue-bound, so packing bits there
+        costs more than the TMA-loaded fp32 mask costs the one dgrad that would use them."""
+        return None if i <= 1 else ws.mbits[i][row0:]
+
+    def forward(self, ws: Workspace, B: int, row0: int = 0, training: bool = True) -> None:
         """X0[row0:row0+B] -> A1, A2, A3 -> F[:, :25600] (bias + LeakyReLU fused in the GEMM epilogue)."""
         for i in range(1, 5):
             x = ws.A[i - 1][row0:]
             y = ws.F[row0:] if i == 4 else ws.A[i][row0:]
-            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], self.flat.p(self.bname(i)), y, EPI_BIAS_LRELU, SLOPE)
+            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], self.flat.p(self.bname(i)), y, EPI_BIAS_LRELU, SLOPE,
+                         mask_bits=self.bits(ws, i, row0) if training else None)
 
     def forward_masked(self, ws: Workspace, B: int, row0: int) -> None:
         """Second-order chain of the gradient penalty: v_k = LeakyReLU'(a_k) * conv_k(v_{k-1}) written in place of
@@ -207,7 +217,7 @@ class ConvStack:
         for i in range(1, 5):
             x = ws.A[i - 1][row0:]
             y = ws.F[row0:] if i == 4 else ws.A[i][row0:]
-            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], None, y, EPI_MASK, SLOPE, mask_src=y)
+            A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], None, y, EPI_MASK, SLOPE, mask_src=y, mask_bits=self.bits(ws, i, row0))
 
     def backward_data(self, ws: Workspace, B: int, row0: int = 0) -> None:
         """delta_4 (= ws.dA[4], already multiplied by LeakyReLU'(a_4)) -> delta_3, delta_2, delta_1 for rows
@@ -215,7 +225,8 @@ class ConvStack:
         dA = ws.grads()
         for i in (4, 3, 2):
             g = conv_geom4_compact(B) if i == 4 else conv_geom(i, B)
-            A.conv_dgrad(g, dA[i][row0:], self.wd[i - 1], dA[i - 1][row0:], ws.A[i - 1][row0:], SLOPE)
+            A.conv_dgrad(g, dA[i][row0:], self.wd[i - 1], dA[i - 1][row0:], ws.A[i - 1][row0:], SLOPE,
+                         mask_bits=self.bits(ws, i - 1, row0))
 
     def input_grad(self, ws: Workspace, B: int, row0: int) -> None:
         """dX0 = conv1^T(delta_1) for rows [row0,row0+B): the dD/dx of algo/wdgail.py:85-91 (normalised-input space)."""

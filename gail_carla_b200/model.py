@@ -86,10 +86,10 @@ class PolicyEngine:
         m = ws.buf("metrics", ws.rows, 4)
         A.gather_rows(metrics_rows, idx, m[row0:], B, 4, 4)
 
-    def forward(self, B: int) -> torch.Tensor:
+    def forward(self, B: int, training: bool = False) -> torch.Tensor:
         """Rows [0,B) of the workspace -> head output [B,4] = {value, mu0_raw, mu1_raw, 0}."""
         ws, P = self.ws, self.flat.p
-        self.conv.forward(ws, B)
+        self.conv.forward(ws, B, training=training)
         A.metrics_features(ws.buf("metrics", ws.rows, 4), P("base.metrics_processor.road_option_embedding.weight"),
                            ws.F[:, E.FEAT:], LDF, 32, B)
         h1 = ws.buf("h1", ws.rows, 512)
@@ -131,7 +131,8 @@ class PolicyEngine:
         A.unprep_fc1_wgrad(self.dw1, 1, G("base.body.body.0.weight"), 512, N_METRIC_FEAT, LDF)
         A.colsum(d, 512, B, 512, G("base.body.body.0.bias"))
         # features: conv part masked by LeakyReLU'(a4) (-> delta_4); metric part feeds the embedding
-        A.linear_dgrad(d, 512, self.w1, LDF, dA[4], E.FEAT, B, E.FEAT, 512, mask_src=ws.F, ldm=LDF, slope=E.SLOPE)
+        A.linear_dgrad(d, 512, self.w1, LDF, dA[4], E.FEAT, B, E.FEAT, 512, mask_src=ws.F, ldm=LDF, slope=E.SLOPE,
+                       mask_bits=ws.mbits[4])
         A.linear_dgrad(d, 512, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, B, 32, 512)
         A.metrics_features_bwd(ws.buf("metrics", ws.rows, 4), ws.dFt, 32, G("base.metrics_processor.road_option_embedding.weight"), B)
         self.conv.backward_data(ws, B)

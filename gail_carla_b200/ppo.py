@@ -81,7 +81,7 @@ class PPO():
                 A.gather_rows(vp_rows, idx, vo_b, B, 1, 1)
                 A.gather_rows(ret_rows, idx, r_b, B, 1, 1)
                 A.gather_rows(lp_rows, idx, lp_b, B, 1, 1)
-                head = eng.forward(B + Be)
+                head = eng.forward(B + Be, training=True)
                 d_head = ws.buf("dhead", ws.rows, 4)
                 A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats, d_head, None, None, acc, B, logstd, act,
                            float(self.clip_param), float(self.value_loss_coef), float(w_act), 0)
@@ -100,8 +100,6 @@ class PPO():
         gail_action_loss = a[1] / (B * n_updates)
         bc_loss = (a[2] / n_bc_rows) if n_bc_rows else 0.0
         action_loss = self.gamma * bc_loss + (1 - self.gamma) * gail_action_loss if use_bc else gail_action_loss
-        if use_bc:
-            bc_loss = a[2] / n_bc_rows * 1.0        # mean over updates of per-update batch means (equal batch sizes)
         entropy = sum(0.5 + 0.5 * math.log(2 * math.pi) + v for v in logstd)
         if self.gamma is not None:
             self.gamma *= self.decay

@@ -87,8 +87,8 @@ class CriticEngine:
         A.small_linear_fwd(H, LDH, P("trunk.2.weight"), P("trunk.2.bias"), d, 1, rows, 1, self.hidden)
         return d
 
-    def forward(self, rows: int) -> torch.Tensor:
-        self.conv.forward(self.ws, rows)
+    def forward(self, rows: int, training: bool = False) -> torch.Tensor:
+        self.conv.forward(self.ws, rows, training=training)
         return self.trunk_forward(rows)
 
     def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0) -> None:
@@ -99,7 +99,7 @@ class CriticEngine:
         # ---- forward over expert | policy | mix-up (algo/wdgail.py:116,121,66-82)
         A.mixup(ws.X0, ws.X0[B:], alpha, ws.X0[2 * B:], B, S2D_PER_SAMPLE)
         self.tail_features(B, 0); self.tail_features(B, B); self.tail_features(B, 2 * B, mix_from=(0, B, alpha))
-        d = self.forward(R)
+        d = self.forward(R, training=True)
         dd = ws.buf("dd", ws.rows)
         A.disc_loss_seed(d, dd, acc, B)                                   # acc[0:4]; seeds -/+tanh'/B and 1
         # ---- backward
@@ -110,7 +110,8 @@ class CriticEngine:
         A.small_linear_bwd(H, LDH, P("trunk.2.weight"), dd, 1, dH, LDH, G("trunk.2.weight"), G("trunk.2.bias"), R, 2 * B, 1,
                            H_, E.SLOPE)
         # delta_4 for all rows; metric/action columns only for the rows that carry loss (expert, policy)
-        A.linear_dgrad(dH, LDH, self.w1, LDF, dA[4], E.FEAT, R, E.FEAT, H_, mask_src=ws.F, ldm=LDF, slope=E.SLOPE)
+        A.linear_dgrad(dH, LDH, self.w1, LDF, dA[4], E.FEAT, R, E.FEAT, H_, mask_src=ws.F, ldm=LDF, slope=E.SLOPE,
+                       mask_bits=ws.mbits[4])
         A.linear_dgrad(dH, LDH, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, 2 * B, 32, H_)
         m = ws.buf("metrics", ws.rows, 4)
         emb_g = G("metrics_processor.road_option_embedding.weight")

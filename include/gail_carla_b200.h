@@ -160,14 +160,20 @@ typedef struct gc_conv_geom {
 #define GC_EPI_BIAS 2
 #define GC_EPI_MASK 3
 
+/* LeakyReLU' bit masks (optional accelerator, all `mask_bits` arguments nullable): one bit per fp32 element of an
+ * activation tensor in the same linear order (word = element offset / 32; channel counts and batch strides must be
+ * multiples of 32).  gc_conv_fprop writes them from its bias+LeakyReLU epilogue (bit = output > 0); the mask epilogues of
+ * gc_conv_fprop / gc_conv_dgrad / gc_linear_dgrad read them instead of TMA-loading the fp32 `mask_src` tile
+ * (semantically identical: mask = mask_src > 0 ? 1 : slope). */
+
 /* nn.Conv2d forward (tools/model.py:137-143) on NHWC: y = epi(conv(x, w)); w in the fprop operand layout
  * [Cout][KH][KW][Cin].  GC_EPI_MASK multiplies by LeakyReLU'(sign of mask_src) instead of adding a bias (used for the
  * second-order chain of the gradient penalty, algo/wdgail.py:85-97). */
-int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const float* bias, const float* mask_src, float* y,
-                  int epilogue, float slope, void* stream);
+int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const float* bias, const float* mask_src,
+                  unsigned* mask_bits, float* y, int epilogue, float slope, void* stream);
 /* data gradient: dx = LeakyReLU'(mask_src) * conv_transpose(dy, w); wd in the dgrad operand layout. */
-int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, float* dx, float slope,
-                  void* stream);
+int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, const unsigned* mask_bits,
+                  float* dx, float slope, void* stream);
 /* weight gradient partials [splits][Cout][KH][KW*Cin]; gc_conv_wgrad_splits suggests `splits` for a geometry. */
 int gc_conv_wgrad_splits(const gc_conv_geom* g);
 int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float* dw_partial, int splits, void* stream);
@@ -176,8 +182,8 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
 int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const float* bias, float* y, long ldy, int M, int N, int K,
                   int epilogue, float slope, int splits, void* stream);
 /* dx[M,N] = LeakyReLU'(mask_src) * dy[M,K] w[K,N]  (w = forward weight [out=K, in=N]). */
-int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, long ldm, float* dx, long lddx,
-                    int M, int N, int K, float slope, void* stream);
+int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, const unsigned* mask_bits,
+                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, void* stream);
 /* dw[z][M,N] = sum_{rows in split z} dy[row,M]^T x[row,N]. */
 int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float* dw, long lddw, int M, int N, int K, int splits,
                     void* stream);

@@ -310,7 +310,7 @@ def _out_view(g, y):
     return _v(y, (g.B, g.OHp, g.OWp, g.Cout), (g.out_batch_stride, g.OWp * g.Cout, g.Cout, 1))
 
 
-def conv_fprop(geom, x, w, bias, y, epilogue, slope=0.2, mask_src=None):
+def conv_fprop(geom, x, w, bias, y, epilogue, slope=0.2, mask_src=None, mask_bits=None):   # mask_bits: accelerator only, ignored
     g = geom
     xin = _in_view(g, x)[:, :g.H, :g.W].permute(0, 3, 1, 2)
     wt = w.reshape(-1)[:g.Cout * g.KH * g.KW * g.Cin].view(g.Cout, g.KH, g.KW, g.Cin).permute(0, 3, 1, 2)
@@ -330,7 +330,7 @@ def _w_from_dgrad_layout(g, wd):
     return t.permute(5, 2, 3, 0, 4, 1).reshape(g.Cout, g.Cin, g.KH, g.KW)                           # n,c,(a,py),(b',px)
 
 
-def conv_dgrad(geom, dy, wd, dx, mask_src=None, slope=0.2):
+def conv_dgrad(geom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None):
     g = geom
     w = _w_from_dgrad_layout(g, wd)
     d = _out_view(g, dy)[:, :g.OH, :g.OW].permute(0, 3, 1, 2)
@@ -371,7 +371,7 @@ def linear_fwd(x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue, slope=0.2, split
     o[0] = r
 
 
-def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2):
+def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None):
     r = _v2(dy, M, K, lddy) @ _v2(w, K, N, ldw)
     if mask_src is not None:
         r = r * _slope_mask(_v2(mask_src, M, N, ldm), slope)
