@@ -410,12 +410,13 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
     }
     p.bit_str[0] = (long)g->S * g->Cin; p.bit_str[1] = (long)g->S * g->Wp * g->Cin; p.bit_str[2] = g->in_batch_stride;
   };
-  // Patch mode for the small layer (conv2): resident weights (all classes, <= 128 KB) and one (8+1)x(16+1) patch of dy per
-  // 32-channel chunk serving the 4 taps (a,b') as shifted A views.
-  if (g->S == 2 && TA == 2 && TB == 2 && (long)Ntot * Kd * 4 <= 131072 && Ntot <= 256 && getenv("GC_NO_PATCH") == nullptr) {
+  // Patch mode for the small layers (conv2, and conv1 in its stride-1 space-to-depth form): resident weights (all classes,
+  // <= 128 KB) and one (8+1)x(16+1) patch of dy per 32-channel chunk serving the 4 taps (a,b') as shifted A views.
+  if ((g->S == 1 || g->S == 2) && TA == 2 && TB == 2 && (long)Ntot * Kd * 4 <= 131072 && Ntot <= 256 && NI >= 8 && NJ >= 16 &&
+      getenv("GC_NO_PATCH") == nullptr) {
     Plan pl;
     GemmParams& p = pl.p;
-    const int nchunk = g->Cout / 32;
+    const int nchunk = g->Cout / 32, S = g->S;
     p.bn = Ntot;
     p.bk = 32;
     p.e0 = cdiv(NI, 8); p.e1 = cdiv(NJ, 16);
@@ -441,19 +442,18 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
       if (int e = make_map(spec(wd, 2, dim, str, box, 1, 1), &p.mapB)) return e;
     }
     p.b_resident = 1; p.b_slabs = 4 * nchunk;
-    const PixBox bx{8, 16, 1};
     const int inner = std::min(32, g->Cin);
-    for (int py = 0; py < 2; ++py) for (int px = 0; px < 2; ++px) {
-      const int cls = py * 2 + px;
+    for (int py = 0; py < S; ++py) for (int px = 0; px < S; ++px) {
+      const int cls = py * S + px;
       const long base = ((long)py * g->Wp + px) * g->Cin;
-      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)cdiv(g->W - px, 2), (uint64_t)cdiv(g->H - py, 2), (uint64_t)g->B};
-      const uint64_t str[4] = {1, (uint64_t)2 * g->Cin, (uint64_t)2 * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
+      const uint64_t dim[4] = {(uint64_t)g->Cin, (uint64_t)cdiv(g->W - px, S), (uint64_t)cdiv(g->H - py, S), (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)S * g->Cin, (uint64_t)S * g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
       const uint32_t box[4] = {(uint32_t)inner, 8, 16, 1};
-      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, 1), &p.mapD[cls])) return e;
-      if (mask_src && !mask_bits) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, 1), &p.mapX[cls])) return e; }
+      if (int e = make_map(spec(dx + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapD[cls])) return e;
+      if (mask_src && !mask_bits) { if (int e = make_map(spec(mask_src + base, 4, dim, str, box, 0, g->Cin >= 32), &p.mapX[cls])) return e; }
       else p.mapX[cls] = p.mapD[cls];
     }
-    p.cols_per_map = g->Cin;
+    p.cols_per_map = ncls > 1 ? g->Cin : 0;
     p.d.mul[1][M0] = 8; p.d.mul[2][M1] = 16; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
     p.d_box_bytes = inner * 4 * 128;
     p.epilogue = want_mask ? EPI_MASK : EPI_STORE; p.slope = slope; p.n_total = Ntot;

@@ -197,44 +197,88 @@ class Discriminator(nn.Module):
             eng.update_step(B, alpha, acc, float(lambda_))
             return (float(lambda_) * acc[4] / B).float()
 
+    def _upload_alpha(self, alpha: torch.Tensor) -> torch.Tensor:
+        """Mix-up coefficients drawn on the host (RNG parity) -> device through a small ring of pinned buffers."""
+        dev = self._dev()
+        if dev.type != "cuda":
+            return alpha
+        ring = getattr(self, "_alpha_ring", None)
+        if ring is None or ring[0][0].numel() != alpha.numel():
+            ring = [[torch.empty(alpha.numel(), pin_memory=True), None] for _ in range(4)]
+            self._alpha_ring, self._alpha_i = ring, 0
+        slot = ring[self._alpha_i]
+        self._alpha_i = (self._alpha_i + 1) % len(ring)
+        if slot[1] is not None:
+            slot[1].synchronize()          # the upload that last used this pinned slot has completed (normally long ago)
+        slot[0].copy_(alpha)
+        out = slot[0].to(dev, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return out
+
     def _prefetched(self, pairs):
-        """Yield (expert tensors on the device, idx) with the host->device copy of the NEXT expert batch issued on a
-        side stream while the current batch is being processed (the expert loader hands out host tensors,
-        algo/wdgail.py:112,119; at B=4096 a batch is 1.8 GB)."""
+        """Yield ``(expert tensors on the device, idx, release)`` for every (expert batch, policy index batch) pair.
+
+        The expert loader hands out host tensors (algo/wdgail.py:112,119; 1.8 GB per batch at B=4096).  They are uploaded
+        on a side stream into two preallocated device staging sets, so the copy of batch i+1 runs while batch i is being
+        processed; ``release()`` (called once the batch has been gathered into the workspace) lets the copy stream reuse
+        that staging set."""
         dev = self._dev()
         if dev.type != "cuda":
             for batch, idx in pairs:
-                yield self._to_dev(*batch), idx
+                yield self._to_dev(*batch), idx, (lambda: None)
             return
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_bufs = [None, None]
         main = torch.cuda.current_stream(dev)
+        trace = getattr(self, "_trace", None)      # diagnostics: list collecting (tag, start_event, end_event)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]
 
-        def stage(pair):
+        def stage(pair, k):
             batch, idx = pair
-            self._copy_stream.wait_stream(main)       # do not overwrite buffers the main stream may still read
+            bufs = self._stage_bufs[k]
+            if bufs is None or any(b.shape != t.shape for b, t in zip(bufs, batch)):
+                bufs = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in batch]
+                self._stage_bufs[k] = bufs
+                self._copy_stream.wait_stream(main)          # fresh buffers: order after whatever main was doing
+            if consumed[k] is not None:
+                self._copy_stream.wait_event(consumed[k])    # the previous tenant of this staging set has been gathered
             with torch.cuda.stream(self._copy_stream):
-                ts = [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in batch]
+                if trace is not None:
+                    c0 = torch.cuda.Event(enable_timing=True); c0.record(self._copy_stream)
+                for b, t in zip(bufs, batch):
+                    b.copy_(t, non_blocking=True)
+                ready[k].record(self._copy_stream)
+                if trace is not None:
+                    c1 = torch.cuda.Event(enable_timing=True); c1.record(self._copy_stream)
+                    trace.append(("copy", c0, c1))
+            return bufs, idx
+
+        def releaser(k):
+            def release():
                 ev = torch.cuda.Event()
-                ev.record(self._copy_stream)
-            return ts, idx, ev
+                ev.record(main)
+                consumed[k] = ev
+            return release
 
         it = iter(pairs)
         try:
-            cur = stage(next(it))
+            cur = stage(next(it), 0)
         except StopIteration:
             return
+        k = 0
         while cur is not None:
             try:
-                nxt = stage(next(it))
+                nxt = stage(next(it), 1 - k)
             except StopIteration:
                 nxt = None
-            ts, idx, ev = cur
-            main.wait_event(ev)
-            for t in ts:
-                t.record_stream(main)
-            yield ts, idx
-            cur = nxt
+            main.wait_event(ready[k])
+            yield cur[0], cur[1], releaser(k)
+            if consumed[k] is None:                          # caller forgot to release: be safe
+                releaser(k)()
+            cur, k = nxt, 1 - k
 
     # ---- algo/wdgail.py:100-147
     def update(self, expert_loader, rollouts):
@@ -245,15 +289,34 @@ class Discriminator(nn.Module):
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
         acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
+        # Mix-up coefficients (algo/wdgail.py:66: torch.rand(B,1,1,1) per batch on the CPU default generator).  All
+        # host->device transfers share one DMA queue, so a small per-batch upload on the compute stream would queue
+        # behind the 1.8 GB expert prefetch and stall compute; when the number of batches is known the draws are made in
+        # the reference's order up front and uploaded once.
+        pairs = zip(expert_loader, rollouts.minibatch_indices(B))
+        alphas = None
+        if hasattr(expert_loader, "__len__") and dev.type == "cuda":
+            first = next(pairs, None)          # advances both iterators exactly like the first zip step (draws randperm)
+            n_batches = min(len(expert_loader), (rollouts.num_steps * rollouts.num_processes) // B) if first is not None else 0
+            if n_batches:
+                host = torch.empty(n_batches, B, pin_memory=True)
+                for i in range(n_batches):
+                    host[i] = torch.rand(B, 1, 1, 1).view(B)
+                alphas = host.to(dev, non_blocking=True)
+            import itertools
+            pairs = itertools.chain([first], pairs) if first is not None else iter(())
         with torch.no_grad():
-            for (e_obs, e_met, e_act), idx in self._prefetched(zip(expert_loader, rollouts.minibatch_indices(B))):
+            for i_batch, ((e_obs, e_met, e_act), idx, release) in enumerate(self._prefetched(pairs)):
                 if e_obs.shape[0] != B:
                     raise ValueError("expert batches must all have expert_loader.batch_size rows (drop_last=True)")
                 eng.workspace(3 * B)
                 eng.load_inputs(e_obs, e_met, e_act, None, B, 0)
+                release()
                 eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
-                alpha = torch.rand(B, 1, 1, 1).view(B)            # algo/wdgail.py:66 - CPU default generator
-                alpha = alpha.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else alpha
+                if alphas is not None and i_batch < alphas.shape[0]:
+                    alpha = alphas[i_batch]
+                else:
+                    alpha = self._upload_alpha(torch.rand(B, 1, 1, 1).view(B))
                 eng.update_step(B, alpha, acc)
                 self.optimizer.step()
                 eng.dirty = True
