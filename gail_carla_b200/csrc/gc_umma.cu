@@ -162,7 +162,7 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     (void)configured;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    kern<<<grid, 192, smem, st>>>(p);
+    kern<<<grid, 320, smem, st>>>(p);
     return gc::launch_status(what);
   };
   if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false>);

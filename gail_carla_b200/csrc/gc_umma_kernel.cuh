@@ -51,7 +51,7 @@ __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -135,12 +135,15 @@ __device__ __forceinline__ void tile_coords(const TmaAddr& t, const int (&src)[k
 }
 
 // Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
-//   warp 4  : TMA producer (one lane) + TMEM owner          -> smem ring (full/empty mbarriers)
-//   warp 5  : tcgen05.mma issuer (one lane)                 -> two TMEM accumulator stages (tmem_full/tmem_empty)
-//   warps 0-3: epilogue, TMEM lanes 32w..32w+31             -> staging smem -> TMA store
-// so the epilogue of tile i overlaps the mainloop of tile i+1 and barrier/TMEM set-up is paid once per SM.
+//   warp 8   : TMA producer (one lane) + TMEM owner          -> smem ring (full/empty mbarriers)
+//   warp 9   : tcgen05.mma issuer (one lane)                 -> two TMEM accumulator stages (tmem_full/tmem_empty)
+//   warps 0-3, 4-7: two epilogue groups (TMEM lanes 32(w%4)..+31); group g drains accumulator stage g, i.e. every
+//              other tile, -> staging smem -> TMA store.  The epilogue is a per-warp dependency chain (~3000 clocks
+//              per 128x32 tile on one group, ncu: profiles/r01_ncu_conv1_fprop_details.txt), so two groups in
+//              ping-pong double its throughput; with TMA-loaded mask tiles (EPI_MASK without bit masks) only group 0 runs.
+// The epilogue of tile i overlaps the mainloop of tile i+1 and barrier/TMEM set-up is paid once per SM.
 template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = p.a_bytes + p.b_bytes;
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     fence_async_smem();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)p.tmem_cols)
                  : "memory");
@@ -185,7 +188,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const uint32_t tx = p.a_panels * p.a_panel_bytes + (p.b_resident ? 0 : p.b_panels * p.b_panel_bytes);
       if (p.b_resident) {  // the whole weight matrix, once per CTA
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
@@ -303,14 +306,21 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
     // Output leaves in 32-column panels through `nbuf` 16 KB staging buffers (a ring over all panels of all tiles
     // of this CTA).  With EPI_MASK the panel's LeakyReLU' source tile (same box geometry as the output) is
     // TMA-loaded into the staging buffer two panels ahead, multiplied in place and stored from the same buffer.
-    const int row = warp * 32 + lane;
+    const int grp = warp >> 2, wq = warp & 3;      // epilogue group, TMEM lane quarter
+    const int row = wq * 32 + lane;
+    const bool leader = (threadIdx.x & 127) == 0;  // issues this group's TMA traffic
     const int n_panels = (p.bn + 31) >> 5;
     const bool swz = p.d_row_bytes == 128;
     const bool masked = p.epilogue == EPI_MASK && p.bits_in == nullptr;  // TMA-loaded mask tiles
     const bool bitmask = p.epilogue == EPI_MASK && p.bits_in != nullptr;
-    const int nbuf = p.nbuf;
+    const bool two_groups = !masked;               // ping-pong on the two accumulator stages, one staging buffer each
+    const int nbuf = two_groups ? 1 : p.nbuf;
+    uint8_t* const my_staging = staging + (two_groups ? grp * 16384 : 0);
+    const int tile_step = two_groups ? 2 * (int)gridDim.x : (int)gridDim.x;
+    const int ti_step = two_groups ? 2 : 1;
+    const bool active = two_groups || grp == 0;
     const int r0 = row % p.row_box[0], r1 = (row / p.row_box[0]) % p.row_box[1], r2 = row / (p.row_box[0] * p.row_box[1]);
-    int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (thread 0 only)
+    int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (group leader only; single-group mode)
     // output panel q of a tile -> which tensor map and which coordinates
     auto out_panel = [&](const int (&base)[5], int n_tile, int q, int (&c)[5]) -> int {
       if (p.cols_per_map > 0) {
@@ -335,11 +345,12 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       ++pf_count;
       if (++pf_q == n_panels) { pf_q = 0; pf_tile += gridDim.x; }
     };
-    if (masked && threadIdx.x == 0) {
+    if (masked && leader && active) {
       for (int i = 0; i < nbuf - 2; ++i) prefetch_one();  // mask prefetch distance = nbuf - 2 panels
     }
-    int pc = 0, ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    int pc = 0;
+    for (int tile = blockIdx.x + (two_groups ? grp * (int)gridDim.x : 0), ti = two_groups ? grp : 0; active && tile < total_tiles;
+         tile += tile_step, ti += ti_step) {
       int src[kSrc], n_tile, cd[5];
       decode_tile(p, tile, src, n_tile);
       tile_coords(p.d, src, cd);
@@ -365,14 +376,18 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
       }
       mbar_wait(tfull0 + 8 * acc, (ti >> 1) & 1);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_cols);
+      const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int q = 0; q < n_panels; ++q, ++pc) {
-        uint8_t* buf = staging + (pc % nbuf) * 16384;
-        if (threadIdx.x == 0) {
-          if (pc >= 2) tma_wait_read<1>();  // the store of panel pc-2 has drained its staging buffer
-          if (masked) prefetch_one();       // panel pc+nbuf-2 -> the buffer the store of panel pc-2 just released
+        uint8_t* buf = my_staging + (pc % nbuf) * 16384;
+        if (leader) {
+          if (two_groups) {
+            tma_wait_read<0>();             // this group's previous store has drained its (single) staging buffer
+          } else {
+            if (pc >= 2) tma_wait_read<1>();  // the store of panel pc-2 has drained its staging buffer
+            if (masked) prefetch_one();       // panel pc+nbuf-2 -> the buffer the store of panel pc-2 just released
+          }
         }
-        epi_bar_sync();
+        epi_bar_sync(grp);
         float v[32];
         tmem_ld32(tacc + (uint32_t)(q * 32), v);
         if (q == n_panels - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -438,8 +453,8 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
           }
         }
         fence_async_smem();
-        epi_bar_sync();
-        if (threadIdx.x == 0) {
+        epi_bar_sync(grp);
+        if (leader) {
           int cq[5];
           const int mi = out_panel(cd, n_tile, q, cq);
           tma_store_5d(&p.mapD[mi], smem_u32(buf), cq);
@@ -447,11 +462,11 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         }
       }
     }
-    if (threadIdx.x == 0) tma_wait_read<0>();
+    if (leader) tma_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
                  : "memory");
   }

@@ -199,9 +199,8 @@ class ConvStack:
 
     @staticmethod
     def bits(ws: Workspace, i: int, row0: int):
-        """LeakyReLU' bit mask of activation i.  A1 has none: conv1's forward is epilogue-bound, so packing bits there
-        costs more than the TMA-loaded fp32 mask costs the one dgrad that would use them."""
-        return None if i <= 1 else ws.mbits[i][row0:]
+        """LeakyReLU' bit mask of activation i (A1, A2, A3 or F), written by the forward epilogues when training."""
+        return None if i < 1 else ws.mbits[i][row0:]
 
     def forward(self, ws: Workspace, B: int, row0: int = 0, training: bool = True) -> None:
         """X0[row0:row0+B] -> A1, A2, A3 -> F[:, :25600] (bias + LeakyReLU fused in the GEMM epilogue)."""
