@@ -119,6 +119,7 @@ struct Plan {
   GemmParams p;
   dim3 grid;
   bool a_mn, b_mn;
+  int b_bytes_override = 0;
   Plan() { memset(&p, 0, sizeof(p)); p.e0 = p.e1 = p.f0 = p.g0 = p.g1 = 1; a_mn = b_mn = false; }
 };
 
@@ -126,7 +127,7 @@ constexpr int kSmemBudget = 225 * 1024;
 
 int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GemmParams& p = pl.p;
-  GC_REQUIRE(p.bn % 16 == 0 && p.bn >= 16 && p.bn <= 256, "%s: tile N %d not a multiple of 16 in [16,256]", what, p.bn);
+  GC_REQUIRE(p.bn % 16 == 0 && p.bn >= 16 && (p.bn <= 256 || p.ngroups > 0), "%s: tile N %d not a multiple of 16 in [16,256]", what, p.bn);
   GC_REQUIRE(p.bk % 8 == 0 && p.bk >= 8, "%s: bk %d not a multiple of 8", what, p.bk);
   if (!pl.a_mn || !pl.b_mn) GC_REQUIRE(p.bk == 32, "%s: K-major operands need bk == 32 (got %d)", what, p.bk);
   if (p.a_bytes == 0) p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
@@ -140,11 +141,14 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   } else {
     p.b_slabs = 0; p.b_slab_bytes = 0;
     p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
+    if (pl.b_bytes_override) p.b_bytes = pl.b_bytes_override;
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
   }
   const int resident = p.b_slabs * p.b_slab_bytes;
   p.nbuf = (p.epilogue == EPI_MASK && p.bits_in == nullptr) ? (p.b_resident ? 3 : 4) : 2;
-  p.tmem_cols = pow2_cols(2 * bpan * 32);  // two accumulator stages
+  if (p.acc_stages == 0) p.acc_stages = 2;
+  p.tmem_cols = pow2_cols(p.acc_stages * bpan * 32);
+  GC_REQUIRE(p.tmem_cols <= 512, "%s: accumulators need %d TMEM columns", what, p.tmem_cols);
   p.d_row_bytes = p.bn >= 32 ? 128 : p.bn * 4;
   const int stage = p.a_bytes + p.b_bytes;
   const int fixed = p.nbuf * 16384 + 4096 + resident;  // staging + barriers/bias/alignment slack + resident weights
@@ -165,9 +169,13 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     kern<<<grid, 320, smem, st>>>(p);
     return gc::launch_status(what);
   };
-  if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false>);
-  if (!pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<false, true>);
-  if (pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<true, true>);
+  if (p.ngroups > 0) {
+    GC_REQUIRE(pl.a_mn && pl.b_mn, "%s: slab mode needs MN-major operands", what);
+    return launch(umma_gemm_kernel<true, true, true>);
+  }
+  if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false, false>);
+  if (!pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<false, true, false>);
+  if (pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<true, true, false>);
   return gc::fail(-2, "%s: unsupported operand majors", what);
 }
 
@@ -531,8 +539,37 @@ static void wgrad_tile_n(const gc_conv_geom* g, int& bn, int& ky_per, int& n_til
   }
 }
 
+// Slab-mode wgrad for the stride-2 4x4 convolutions.  With both dY and the four input parity sub-images flattened to
+// rows of pitch P (> OW, zero-filled by TMA beyond the extents), tap (ky,kx) = (2a+py, 2b+px) is a 1-D correlation:
+//   dW[n][ky][kx][c] = sum_r dY[r][n] * Xsub_{py,px}[r + a*P + b][c]
+// so ONE patch per parity class serves its 4 taps as MN-major B views shifted by a*P+b rows (the b=0/b=1 panels are the
+// same rows one apart: LBO = 128 B), and dY is fetched once for all 16 taps of a 32-channel chunk.  The wrap-around
+// products of the shift hit the zero columns of dY.  (MN-major shifted views: profiles/r01_umma_descriptor_experiment.txt.)
+struct SlabGeom { int P, by, R, rows_patch; bool ok; };
+static SlabGeom slab_geom(const gc_conv_geom* g) {
+  SlabGeom s{0, 0, 0, 0, false};
+  if (!(g->S == 2 && g->KH == 4 && g->KW == 4 && g->Cin % 32 == 0 && g->Cout % 32 == 0 && g->Wp % 2 == 0 && g->Hp % 2 == 0)) return s;
+  if (getenv("GC_NO_SLAB") != nullptr) return s;
+  s.P = ((g->OW + 1 + 3) / 4) * 4;
+  if (s.P > 256 || s.P > g->Wp / 2 + 8) return s;
+  for (int by = 1; by <= 8; ++by) {
+    if ((s.P * by) % 8) continue;
+    const int a_bytes = std::min(4, g->Cout / 32) * s.P * by * 128, b_bytes = 4 * (by + 2) * s.P * 128;
+    if (2 * (a_bytes + b_bytes) + 2 * 16384 + 4096 > kSmemBudget) break;   // keep >= 2 pipeline stages
+    s.by = by;
+    if (s.P * by >= 48) break;
+  }
+  if (s.by == 0) return s;
+  s.R = s.P * s.by; s.rows_patch = (s.by + 2) * s.P; s.ok = true;
+  return s;
+}
+
 int gc_conv_wgrad_splits(const gc_conv_geom* g) {
   if (check_geom(g, "gc_conv_wgrad_splits")) return -1;
+  if (slab_geom(g).ok) {
+    const int tiles = cdiv(g->Cout, 128) * (g->Cin / 32);
+    return std::max(1, std::min(g->B, (2 * gc::kNumSMs) / std::max(1, tiles)));
+  }
   int bn, ky_per, n_tiles;
   wgrad_tile_n(g, bn, ky_per, n_tiles);
   const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(bn), 8, 4.0);
@@ -548,6 +585,67 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
   GC_REQUIRE(dy && x && dw_partial, "gc_conv_wgrad: null pointer");
   GC_REQUIRE(g->Cout % 32 == 0, "gc_conv_wgrad: Cout %% 32 required");
   GC_REQUIRE(splits >= 1, "gc_conv_wgrad: splits=%d", splits);
+  const SlabGeom sg = slab_geom(g);
+  if (sg.ok) {
+    Plan pl;
+    GemmParams& p = pl.p;
+    pl.a_mn = pl.b_mn = true;
+    const int C = g->Cin, KC = 4 * C;
+    p.bn = 512; p.mma_n = 64; p.acc_stages = 1; p.ngroups = 8;
+    p.bk = sg.R;
+    p.e0 = cdiv(g->Cout, 128); p.e1 = 1;
+    p.f0 = C / 32;                              // n-tile = 32-channel chunk
+    p.g0 = cdiv(g->OH, sg.by);                  // k -> (row tile, sample within the split)
+    const int per_split = cdiv(g->B, splits);
+    p.g1 = per_split;
+    p.k_iters = p.g0 * per_split;
+    // A: dY rows (ox padded to P, zero-filled), panels of 32 output channels
+    {
+      const uint64_t dim[4] = {(uint64_t)g->Cout, (uint64_t)g->OW, (uint64_t)g->OH, (uint64_t)g->B};
+      const uint64_t str[4] = {1, (uint64_t)g->Cout, (uint64_t)g->OWp * g->Cout, (uint64_t)g->out_batch_stride};
+      const uint32_t box[4] = {32, (uint32_t)sg.P, (uint32_t)sg.by, 1};
+      if (int e = make_map(spec(dy, 4, dim, str, box, 1, 2), &p.mapA)) return e;
+    }
+    p.a.mul[0][M0] = 128; p.a.mul[2][K0] = sg.by; p.a.mul[3][K1] = 1; p.a.mul[3][Z] = per_split; p.a.panel[0] = 32;
+    p.a_panels = std::min(4, g->Cout / 32); p.a_panel_bytes = sg.R * 128; p.a_bytes = p.a_panels * sg.R * 128;
+    p.a_bytes = (p.a_bytes + 1023) & ~1023;
+    // B: one patch per parity class (py,px) of the input, (by+2) rows of pitch P
+    {
+      const uint64_t dim[5] = {(uint64_t)2 * C, (uint64_t)g->Wp / 2, 2, (uint64_t)g->Hp / 2, (uint64_t)g->B};
+      const uint64_t str[5] = {1, (uint64_t)2 * C, (uint64_t)g->Wp * C, (uint64_t)2 * g->Wp * C, (uint64_t)g->in_batch_stride};
+      const uint32_t box[5] = {32, (uint32_t)sg.P, 1, (uint32_t)sg.by + 2, 1};
+      if (int e = make_map(spec(x, 5, dim, str, box, 1, 2), &p.mapB)) return e;
+    }
+    p.b.mul[0][N0] = 32; p.b.mul[3][K0] = sg.by; p.b.mul[4][K1] = 1; p.b.mul[4][Z] = per_split;
+    p.b.panel[0] = C; p.b.panel2[2] = 1; p.b.period = 2;       // class cls = py*2+px: px -> +C in dim 0, py -> +1 in dim 2
+    p.b_panels = 4; p.b_panel_bytes = sg.rows_patch * 128;
+    pl.b_bytes_override = 4 * sg.rows_patch * 128;
+    p.exp_b_lbo = 128;                                          // panels b=0 / b=1 of a group: same rows, one apart
+    for (int cls = 0; cls < 4; ++cls) for (int a = 0; a < 2; ++a) {
+      const int gi = cls * 2 + a;
+      p.grp_b_off[gi] = cls * p.b_panel_bytes + a * sg.P * 128;
+      p.grp_acc[gi] = gi * 64;
+      for (int b = 0; b < 2; ++b) {
+        const int py = cls / 2, px = cls % 2;
+        p.panel_tab0[gi * 2 + b] = (2 * b + px) * C;            // kx * C (+ 32*chunk from the tile)
+        p.panel_tab1[gi * 2 + b] = 2 * a + py;                  // ky
+      }
+    }
+    // D: partial[z][Cout][KH][KW*C]
+    {
+      const uint64_t dim[4] = {(uint64_t)KC, (uint64_t)g->KH, (uint64_t)g->Cout, (uint64_t)splits};
+      const uint64_t str[4] = {1, (uint64_t)KC, (uint64_t)g->KH * KC, (uint64_t)g->Cout * g->KH * KC};
+      const int rows = std::min(128, g->Cout);
+      const uint32_t box[4] = {32, 1, (uint32_t)rows, 1};
+      if (int e = make_map(spec(dw_partial, 4, dim, str, box, 0, 1), &p.mapD[0])) return e;
+      p.d_box_bytes = rows * 128;
+    }
+    p.mapX[0] = p.mapD[0];
+    p.d.mul[0][N0] = 32; p.d.mul[2][M0] = 128; p.d.mul[3][Z] = 1;
+    p.epilogue = EPI_STORE; p.n_total = 16 * C;
+    pl.grid = dim3(p.e0, p.f0, splits);
+    return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_wgrad(slab)");
+  }
   Plan pl;
   GemmParams& p = pl.p;
   pl.a_mn = pl.b_mn = true;
@@ -731,6 +829,20 @@ int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float*
     if (int e = make_map(spec(x, 2, dim, str, box, 1, 2), &p.mapB)) return e;
   }
   p.b.mul[0][N0] = p.bn; p.b.mul[1][K0] = p.bk; p.b.panel[0] = 32; p.b_panels = p.bn / 32; p.b_panel_bytes = p.bk * 128;
+  if (const char* ex = getenv("GC_EXP")) {
+    // Bring-up experiment (tests/gpu_probe_desc.py): MN-major (SWIZZLE_128B_BASE32B) B views that start r rows into the
+    // loaded panel (mode 3), and two 32-column panels that are the SAME rows one row apart (LBO = 128 B, mode 4).
+    int mode = 0, r = 0, bo = 0;
+    if (sscanf(ex, "%d,%d,%d", &mode, &r, &bo) == 3 && (mode == 3 || mode == 4)) {
+      const uint64_t dim[2] = {(uint64_t)N, (uint64_t)K}, str[2] = {1, (uint64_t)ldx};
+      const uint32_t box[2] = {32, (uint32_t)p.bk + 8};
+      if (int e = make_map(spec(x, 2, dim, str, box, 1, 2), &p.mapB)) return e;
+      p.b_panel_bytes = (p.bk + 8) * 128;
+      p.exp_b_off = r * 128;
+      if (mode == 4) { p.b_panels = 1; p.exp_b_lbo = 128; }
+      pl.b_bytes_override = (p.bn / 32) * (p.bk + 8) * 128;
+    }
+  }
   {
     const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)lddw, (uint64_t)lddw * M};
     const uint32_t box[3] = {32, 128, 1};

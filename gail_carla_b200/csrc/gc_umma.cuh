@@ -54,6 +54,7 @@ struct alignas(64) GemmParams {
   int nbuf;            // staging buffers: 2, or 4 with EPI_MASK
   int cols_per_map;    // > 0: output column c goes to map c / cols_per_map at channel c % cols_per_map (merged dgrad)
   int exp_a_off, exp_a_sbo, exp_a_baseoff;  // bring-up experiment hooks for the A descriptor (0 = normal)
+  int exp_b_off, exp_b_lbo;                 // same for the B descriptor (MN-major shifted-view experiments)
   // patch mode: one TMA-loaded input patch per stage serves `taps` shifted A views (convolution taps); B (the whole
   // weight matrix) is loaded once per CTA and stays resident in shared memory.
   int taps;             // MMA groups per stage (1 = plain GEMM)
@@ -62,6 +63,14 @@ struct alignas(64) GemmParams {
   int b_slabs;          // resident 32-wide K slabs
   int b_slab_bytes;     // bn * 128
   unsigned char b_tab[64];  // resident slab used by (k-iteration, tap): b_tab[k * taps + t]
+  // slab mode (wgrad): one A slab per stage is multiplied with `ngroups` shifted views of the B patches, each an
+  // independent mma_n-wide MMA into its own TMEM column block; the tile's bn columns are the union of the blocks.
+  int ngroups;              // 0 = off
+  int grp_b_off[16];        // byte offset of each group's B view inside the stage's B region
+  int grp_acc[16];          // TMEM column offset of each group's accumulator block
+  int mma_n;                // N of one MMA (0 = bn)
+  int acc_stages;           // TMEM accumulator stages: 2, or 1 when bn > 256
+  int panel_tab0[16], panel_tab1[16];  // slab mode: output panel q -> added to output coordinates 0 and 1
   // LeakyReLU' bitmask (1 bit per fp32 element of an activation tensor, same linear order): written by the
   // bias+LeakyReLU epilogue, read by EPI_MASK instead of TMA-loading the fp32 activation tile.
   unsigned* bits_out;        // nullable

@@ -142,7 +142,7 @@ __device__ __forceinline__ void tile_coords(const TmaAddr& t, const int (&src)[k
 //              per 128x32 tile on one group, ncu: profiles/r01_ncu_conv1_fprop_details.txt), so two groups in
 //              ping-pong double its throughput; with TMA-loaded mask tiles (EPI_MASK without bit masks) only group 0 runs.
 // The epilogue of tile i overlaps the mainloop of tile i+1 and barrier/TMEM set-up is paid once per SM.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool SLAB>
 __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16, aux0 = tempty0 + 16, bres_bar = aux0 + 32;
   const int total_tiles = p.mt * p.nt * p.zt;
   const int acc_cols = ((p.bn + 31) >> 5) << 5;
+  const int acc_stages = p.acc_stages;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -246,10 +247,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+                             ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) | ((128u >> 4) << 24);
       const int ksteps = p.bk >> 3;
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
-      const uint32_t b_lbo = B_MN ? (uint32_t)p.b_panel_bytes : 0u;
+      const uint32_t b_lbo = p.exp_b_lbo ? (uint32_t)p.exp_b_lbo : (B_MN ? (uint32_t)p.b_panel_bytes : 0u);
       int it = 0, ti = 0;
       const uint32_t a_sbo = p.exp_a_sbo ? (uint32_t)p.exp_a_sbo : (A_MN ? 512u : 1024u);
       // constant descriptor halves (see umma_desc): lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version | base_offset | layout
@@ -269,8 +270,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int acc = ti & 1;
-        mbar_wait(tempty0 + 8 * acc, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+        const int acc = ti % acc_stages;
+        mbar_wait(tempty0 + 8 * acc, ((ti / acc_stages) & 1) ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(acc * acc_cols);
         for (int k = 0; k < p.k_iters; ++k, ++it) {
@@ -282,9 +283,19 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           // Descriptors differ only in their 14-bit start-address field, so the loop adds to precomputed 32-bit
           // halves; the 4 K-steps of a 128-byte K-major slab are unrolled (the MMA of a 128xN tile with small N takes
           // only N/2 cycles, so the single issuing thread must not spend more than that per instruction).
+          if constexpr (SLAB) {
+            // slab mode: every group multiplies the same A slab with its own shifted view of the B patches
+            const uint32_t alo = a_lo_base + (sa >> 4);
+            for (int g = 0; g < p.ngroups; ++g) {
+              const uint32_t blo = b_lo_base + ((sb + (uint32_t)p.grp_b_off[g]) >> 4);
+              const uint32_t tg = tacc + (uint32_t)p.grp_acc[g];
+              for (int ks = 0; ks < ksteps; ++ks)
+                umma_tf32(tg, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
+            }
+          } else {
           for (int t = 0; t < n_taps; ++t) {
             const uint32_t alo = a_lo_base + ((sa + a_off0 + (uint32_t)tap_off[t]) >> 4);
-            const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[k * n_taps + t] * b_slab : sb) >> 4);
+            const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[k * n_taps + t] * b_slab : sb + (uint32_t)p.exp_b_off) >> 4);
             if (ksteps == 4) {
               umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
               umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
               for (int ks = 0; ks < ksteps; ++ks)
                 umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | t | ks) ? 1u : 0u);
             }
+          }
           }
           umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
         }
@@ -313,7 +325,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const bool swz = p.d_row_bytes == 128;
     const bool masked = p.epilogue == EPI_MASK && p.bits_in == nullptr;  // TMA-loaded mask tiles
     const bool bitmask = p.epilogue == EPI_MASK && p.bits_in != nullptr;
-    const bool two_groups = !masked;               // ping-pong on the two accumulator stages, one staging buffer each
+    const bool two_groups = !masked && acc_stages == 2;  // ping-pong on the two accumulator stages, one staging buffer each
     const int nbuf = two_groups ? 1 : p.nbuf;
     uint8_t* const my_staging = staging + (two_groups ? grp * 16384 : 0);
     const int tile_step = two_groups ? 2 * (int)gridDim.x : (int)gridDim.x;
@@ -329,6 +341,13 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         for (int d = 0; d < 5; ++d) c[d] = base[d];
         c[0] = p.d.off[0] + col % p.cols_per_map;
         return col / p.cols_per_map;
+      }
+      if constexpr (SLAB) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = base[d];
+        c[0] += p.panel_tab0[q];
+        c[1] += p.panel_tab1[q];
+        return 0;
       }
       panel_coords(p.d, base, q, c);
       return 0;
@@ -354,7 +373,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       int src[kSrc], n_tile, cd[5];
       decode_tile(p, tile, src, n_tile);
       tile_coords(p.d, src, cd);
-      const int acc = ti & 1;
+      const int acc = ti % acc_stages;
       // element offset (in the tensor the bitmask describes) of this thread's row in panel q, or -1 if the row is clipped
       auto bit_word = [&](int q) -> long {
         int cq[5];
@@ -374,7 +393,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           }
         }
       }
-      mbar_wait(tfull0 + 8 * acc, (ti >> 1) & 1);
+      mbar_wait(tfull0 + 8 * acc, (ti / acc_stages) & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int q = 0; q < n_panels; ++q, ++pc) {
