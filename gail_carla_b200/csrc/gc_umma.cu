@@ -550,6 +550,7 @@ static SlabGeom slab_geom(const gc_conv_geom* g) {
   SlabGeom s{0, 0, 0, 0, false};
   if (!(g->S == 2 && g->KH == 4 && g->KW == 4 && g->Cin % 32 == 0 && g->Cout % 32 == 0 && g->Wp % 2 == 0 && g->Hp % 2 == 0)) return s;
   if (getenv("GC_NO_SLAB") != nullptr) return s;
+  if (g->OW * g->OH < 400) return s;   // tiny images (conv4: 10x10) lose more to row padding than the patches save
   s.P = ((g->OW + 1 + 3) / 4) * 4;
   if (s.P > 256 || s.P > g->Wp / 2 + 8) return s;
   for (int by = 1; by <= 8; ++by) {
