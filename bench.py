@@ -35,6 +35,9 @@ CONFIGS = {
                workload="configs[3]: full PPO+WDGAIL update epoch, 64 envs x 1024 steps, B=4096"),
     "c5": dict(T=512, N=256, B_ppo=4096, B_gail=4096, ppo_epoch=10, gail_epoch=1,
                workload="configs[4]: 256 envs x 512 steps, 10 PPO epochs x 32 minibatches"),
+    # same batch shapes as c4 with 1/8 of the rollout: used for the ncu launch list (profiles/)
+    "c4s": dict(T=128, N=64, B_ppo=4096, B_gail=4096, ppo_epoch=1, gail_epoch=1,
+                workload="c4 batch shapes on a 64 envs x 128 steps rollout (profiling)"),
     "tiny": dict(T=64, N=8, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1, workload="tiny: 8 envs x 64 steps, B=128"),
     # the bounded sample the CPU arm runs: configs[0] verbatim
     "c1": dict(T=128, N=1, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1,

@@ -157,6 +157,14 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B, fixed %d B)", what, stage, fixed);
   p.stages = stages;
   p.mt = pl.grid.x; p.nt = pl.grid.y; p.zt = pl.grid.z;
+  // the kernel walks tiles as mixed-radix digits (m0 m1 m2 | n0 n1 | z): the radices must nest exactly
+  GC_REQUIRE(p.mt % (p.e0 * p.e1) == 0 && p.nt % p.f0 == 0, "%s: tile grid %dx%d does not nest in (%d,%d | %d)", what, p.mt, p.nt,
+             p.e0, p.e1, p.f0);
+  if (p.cols_per_map > 0) {
+    GC_REQUIRE((p.cols_per_map & (p.cols_per_map - 1)) == 0, "%s: cols_per_map %d must be a power of two", what, p.cols_per_map);
+    p.cpm_shift = 0;
+    while ((1 << p.cpm_shift) < p.cols_per_map) ++p.cpm_shift;
+  }
   const long total_tiles = (long)p.mt * p.nt * p.zt;
   GC_REQUIRE(total_tiles > 0 && total_tiles < (1L << 31), "%s: bad tile count", what);
   const dim3 grid((unsigned)std::min<long>(total_tiles, gc::kNumSMs), 1, 1);
@@ -166,7 +174,24 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     (void)configured;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    static long long* d_stats = nullptr;   // debug only: GC_UMMA_STATS=1 prints where each role of the kernel waits
+    static const bool want_stats = getenv("GC_UMMA_STATS") != nullptr;
+    if (want_stats) {
+      if (!d_stats) cudaMalloc(&d_stats, gc::kNumSMs * 8 * sizeof(long long));
+      cudaMemsetAsync(d_stats, 0, gc::kNumSMs * 8 * sizeof(long long), st);
+      p.stats = d_stats;
+    }
     kern<<<grid, 320, smem, st>>>(p);
+    if (want_stats) {
+      long long h[gc::kNumSMs * 8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
+      double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (unsigned c = 0; c < grid.x; ++c) for (int i = 0; i < 8; ++i) m[i] += (double)h[c * 8 + i] / grid.x;
+      fprintf(stderr, "[umma-stats] %-26s ctas=%u tiles/cta=%.1f k_iters=%d bn=%d stages=%d | clocks/cta total=%.0f prod_wait_empty=%.0f "
+                      "mma_wait_full=%.0f mma_wait_tmem=%.0f epi0_wait_acc=%.0f epi1_wait_acc=%.0f epi0_total=%.0f\n",
+              what, grid.x, m[7], p.k_iters, p.bn, p.stages, m[5], m[0], m[1], m[2], m[3], m[4], m[6]);
+    }
     return gc::launch_status(what);
   };
   if (p.ngroups > 0) {

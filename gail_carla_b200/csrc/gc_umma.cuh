@@ -52,7 +52,8 @@ struct alignas(64) GemmParams {
   int d_row_bytes;     // 128 (swizzled staging) or bn*4 when bn < 32 (unswizzled)
   int d_box_bytes;     // bytes of one output / mask TMA box (rows may be < 128)
   int nbuf;            // staging buffers: 2, or 4 with EPI_MASK
-  int cols_per_map;    // > 0: output column c goes to map c / cols_per_map at channel c % cols_per_map (merged dgrad)
+  int cols_per_map;    // > 0: output column c goes to map c / cols_per_map at channel c % cols_per_map (merged dgrad); power of 2
+  int cpm_shift;       // log2(cols_per_map)
   int exp_a_off, exp_a_sbo, exp_a_baseoff;  // bring-up experiment hooks for the A descriptor (0 = normal)
   int exp_b_off, exp_b_lbo;                 // same for the B descriptor (MN-major shifted-view experiments)
   // patch mode: one TMA-loaded input patch per stage serves `taps` shifted A views (convolution taps); B (the whole
@@ -82,6 +83,8 @@ struct alignas(64) GemmParams {
   long bit_base[4];          // element offset of each output map's origin in that tensor
   float slope;
   const float* bias;
+  // debug (GC_UMMA_STATS=1): per-CTA clocks each role spent waiting on its barriers, 8 counters per CTA; nullptr = off
+  long long* stats;
 };
 
 }  // namespace gcu

@@ -34,6 +34,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// same, accumulating the clocks spent waiting when the debug counters are on
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool timed, long long& acc) {
+  if (timed) {
+    const long long t = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t;
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, const int (&c)[5]) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -93,6 +104,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync tells the compiler that exactly one thread runs the
+// guarded region, so tcgen05.mma / TMA operands go straight to uniform registers instead of through a per-instruction
+// ELECT / R2UR.BROADCAST / BRA.U.ANY serialisation loop (~100 clocks per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 __device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc], int lo, int hi, int (&c)[5]) {
@@ -134,6 +158,61 @@ __device__ __forceinline__ void tile_coords(const TmaAddr& t, const int (&src)[k
   coords(t, src, Z, Z + 1, c);
 }
 
+// Division-free walk over this CTA's tiles.  A lone producer / MMA / epilogue thread pays ~200 clocks of dependent
+// latency per runtime integer division (profiles/r01_umma_role_stats.txt: ~800-1000 clocks of scalar overhead per
+// k-iteration before this), so the tile index is kept as mixed-radix digits (m0 m1 m2 | n0 n1 | z) and advanced by
+// adding the digits of the stride with carries; the only divisions left run once per kernel.
+struct TileWalk {
+  int dig[6], step[6], rad[5];
+  int tile, tstep;
+};
+__device__ __forceinline__ void walk_digits(const GemmParams& p, int x, int (&d)[6]) {
+  const int m = x % p.mt, r = x / p.mt;
+  const int n = r % p.nt;
+  d[5] = r / p.nt;
+  d[0] = m % p.e0;
+  const int t = m / p.e0;
+  d[1] = t % p.e1;
+  d[2] = t / p.e1;
+  d[3] = n % p.f0;
+  d[4] = n / p.f0;
+}
+__device__ __forceinline__ void walk_init(TileWalk& w, const GemmParams& p, int start, int step) {
+  walk_digits(p, start, w.dig);
+  walk_digits(p, step, w.step);
+  w.rad[0] = p.e0; w.rad[1] = p.e1; w.rad[2] = p.mt / (p.e0 * p.e1); w.rad[3] = p.f0; w.rad[4] = p.nt / p.f0;
+  w.tile = start;
+  w.tstep = step;
+}
+__device__ __forceinline__ void walk_next(TileWalk& w) {
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = w.dig[i] + w.step[i] + c;
+    c = v >= w.rad[i] ? 1 : 0;
+    w.dig[i] = c ? v - w.rad[i] : v;
+  }
+  w.dig[5] += w.step[5] + c;
+  w.tile += w.tstep;
+}
+__device__ __forceinline__ void walk_src(const TileWalk& w, const GemmParams& p, int (&src)[kSrc], int& n_tile) {
+  src[M0] = w.dig[0]; src[M1] = w.dig[1]; src[M2] = w.dig[2];
+  src[N0] = w.dig[3]; src[N1] = w.dig[4];
+  src[K0] = src[K1] = src[K2] = 0;
+  src[Z] = w.dig[5];
+  n_tile = w.dig[4] * p.f0 + w.dig[3];
+}
+// per-k-iteration coordinate increments of an operand: k0 advances | k0 wraps, k1 advances | k0 and k1 wrap, k2 advances
+__device__ __forceinline__ void k_deltas(const TmaAddr& t, int g0, int g1, int (&d0)[5], int (&d1)[5], int (&d2)[5]) {
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    const unsigned back0 = (unsigned)(g0 - 1) * (unsigned)t.mul[d][K0], back1 = (unsigned)(g1 - 1) * (unsigned)t.mul[d][K1];
+    d0[d] = t.mul[d][K0];
+    d1[d] = (int)((unsigned)t.mul[d][K1] - back0);
+    d2[d] = (int)((unsigned)t.mul[d][K2] - back1 - back0);
+  }
+}
+
 // Persistent, warp-specialised: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 //   warp 8   : TMA producer (one lane) + TMEM owner          -> smem ring (full/empty mbarriers)
 //   warp 9   : tcgen05.mma issuer (one lane)                 -> two TMEM accumulator stages (tmem_full/tmem_empty)
@@ -154,12 +233,13 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 9);
   float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // nt*bn floats (<= 512) for bias epilogues
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
   const uint32_t tfull0 = empty0 + 8 * p.stages, tempty0 = tfull0 + 16, aux0 = tempty0 + 16, bres_bar = aux0 + 32;
   const int total_tiles = p.mt * p.nt * p.zt;
   const int acc_cols = ((p.bn + 31) >> 5) << 5;
   const int acc_stages = p.acc_stages;
+  const bool timed = p.stats != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -190,7 +270,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t tx = p.a_panels * p.a_panel_bytes + (p.b_resident ? 0 : p.b_panels * p.b_panel_bytes);
       if (p.b_resident) {  // the whole weight matrix, once per CTA
         mbar_expect_tx(bres_bar, (uint32_t)(p.b_slabs * p.b_slab_bytes));
@@ -199,59 +279,97 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           tma_load_5d(smem_u32(bres) + s * p.b_slab_bytes, &p.mapB, bres_bar, cw);
         }
       }
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int src[kSrc], n_tile, baseA[5], baseB[5];
-        decode_tile(p, tile, src, n_tile);
-        tile_coords(p.a, src, baseA);
-        tile_coords(p.b, src, baseB);
-        for (int k = 0; k < p.k_iters; ++k, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+      long long w_empty = 0;
+      int s = 0;
+      uint32_t ph = 0;
+      int da0[5], da1[5], da2[5], db0[5], db1[5], db2[5];
+      k_deltas(p.a, p.g0, p.g1, da0, da1, da2);
+      k_deltas(p.b, p.g0, p.g1, db0, db1, db2);
+      const int a_panels = p.a_panels, b_panels = p.b_resident ? 0 : p.b_panels, b_period = p.b.period;
+      const int k_iters = p.k_iters, stages = p.stages, g0 = p.g0, g1 = p.g1;
+      int pa[5], pb[5], pb2[5];
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        pa[d] = p.a.panel[d];
+        pb[d] = p.b.panel[d];
+        pb2[d] = p.b.panel2[d] - (b_period - 1) * p.b.panel[d];
+      }
+      TileWalk w;
+      walk_init(w, p, blockIdx.x, gridDim.x);
+      for (; w.tile < total_tiles; walk_next(w)) {
+        int src[kSrc], n_tile, ca[5], cb[5];
+        walk_src(w, p, src, n_tile);
+        int k0 = 0, k1 = 0;
+        if (p.kz_stride != 0) {  // flat split-K: this tile starts at k-iteration z * kz_stride
+          const int kit = src[Z] * p.kz_stride;
+          k0 = kit % g0;
+          const int t = kit / g0;
+          k1 = t % g1;
+          src[K0] = k0; src[K1] = k1; src[K2] = t / g1;
+        }
+#pragma unroll
+        for (int d = 0; d < 5; ++d) { ca[d] = p.a.off[d]; cb[d] = p.b.off[d]; }
+        coords(p.a, src, 0, kSrc, ca);
+        coords(p.b, src, 0, kSrc, cb);
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait_t(empty0 + 8 * s, ph ^ 1, timed, w_empty);
           mbar_expect_tx(full0 + 8 * s, tx);
-          const int kit = k + src[Z] * p.kz_stride;
-          src[K0] = kit % p.g0;
-          const int t = kit / p.g0;
-          src[K1] = t % p.g1;
-          src[K2] = t / p.g1;
-          int ca[5], cb[5];
-#pragma unroll
-          for (int d = 0; d < 5; ++d) { ca[d] = baseA[d]; cb[d] = baseB[d]; }
-          coords(p.a, src, K0, K2 + 1, ca);
-          coords(p.b, src, K0, K2 + 1, cb);
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+          const uint32_t sa = smem_u32(smem) + (uint32_t)s * (uint32_t)stage_bytes, sb = sa + p.a_bytes;
           // panels are walked incrementally (no div/mod on the single producer thread's critical path)
-          for (int q = 0; q < p.a_panels; ++q) {
-            tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, ca);
+          int cq[5];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) ca[d] += p.a.panel[d];
+          for (int d = 0; d < 5; ++d) cq[d] = ca[d];
+          for (int q = 0; q < a_panels; ++q) {
+            tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, cq);
+#pragma unroll
+            for (int d = 0; d < 5; ++d) cq[d] += pa[d];
           }
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cq[d] = cb[d];
           int q1 = 0;
-          for (int q = 0; q < (p.b_resident ? 0 : p.b_panels); ++q) {
-            tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cb);
-            if (++q1 == p.b.period) {
+          for (int q = 0; q < b_panels; ++q) {
+            tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cq);
+            if (++q1 == b_period) {
               q1 = 0;
 #pragma unroll
-              for (int d = 0; d < 5; ++d) cb[d] += p.b.panel2[d] - (p.b.period - 1) * p.b.panel[d];
+              for (int d = 0; d < 5; ++d) cq[d] += pb2[d];
             } else {
 #pragma unroll
-              for (int d = 0; d < 5; ++d) cb[d] += p.b.panel[d];
+              for (int d = 0; d < 5; ++d) cq[d] += pb[d];
             }
           }
+          // next k-iteration: (k0, k1, k2) advance as mixed-radix digits, the coordinates by the matching increments
+          if (++k0 == g0) {
+            k0 = 0;
+            if (++k1 == g1) {
+              k1 = 0;
+#pragma unroll
+              for (int d = 0; d < 5; ++d) { ca[d] += da2[d]; cb[d] += db2[d]; }
+            } else {
+#pragma unroll
+              for (int d = 0; d < 5; ++d) { ca[d] += da1[d]; cb[d] += db1[d]; }
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) { ca[d] += da0[d]; cb[d] += db0[d]; }
+          }
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
+      if (timed) p.stats[blockIdx.x * 8 + 0] = w_empty;
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (lane == 0) {
+    if (elect_one()) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) | ((128u >> 4) << 24);
       const int ksteps = p.bk >> 3;
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
       const uint32_t b_lbo = p.exp_b_lbo ? (uint32_t)p.exp_b_lbo : (B_MN ? (uint32_t)p.b_panel_bytes : 0u);
-      int it = 0, ti = 0;
+      int ti = 0;
+      long long w_full = 0, w_tempty = 0;
+      const long long t_start = timed ? clock64() : 0;
       const uint32_t a_sbo = p.exp_a_sbo ? (uint32_t)p.exp_a_sbo : (A_MN ? 512u : 1024u);
       // constant descriptor halves (see umma_desc): lo = start>>4 | LBO>>4 << 16, hi = SBO>>4 | version | base_offset | layout
       const uint64_t a_proto = umma_desc(0, a_lbo, a_sbo, A_MN ? 1 : 2) | ((uint64_t)(p.exp_a_baseoff & 7) << 49);
@@ -262,6 +380,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       const int n_taps = p.taps;
       const bool b_res = p.b_resident != 0;
       const uint32_t bres_u32 = smem_u32(bres), b_slab = (uint32_t)p.b_slab_bytes, a_off0 = (uint32_t)p.exp_a_off;
+      const uint32_t smem0 = smem_u32(smem), a_bytes = (uint32_t)p.a_bytes, b_off = (uint32_t)p.exp_b_off;
+      const int k_iters = p.k_iters, stages = p.stages, ngroups = p.ngroups;
       int tap_off[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) tap_off[t] = p.tap_off[t];
@@ -269,47 +389,56 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         mbar_wait(bres_bar, 0);
         tc_fence_after();
       }
+      // stage ring and accumulator ring positions are counters, not it % stages (no divisions on this thread)
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int acc = ti % acc_stages;
-        mbar_wait(tempty0 + 8 * acc, ((ti / acc_stages) & 1) ^ 1);  // epilogue has drained this accumulator stage
+        mbar_wait_t(tempty0 + 8 * acc, aph ^ 1, timed, w_tempty);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(acc * acc_cols);
-        for (int k = 0; k < p.k_iters; ++k, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1;
-          mbar_wait(full0 + 8 * s, ph);
+        int kt = 0;
+        for (int k = 0; k < k_iters; ++k, kt += n_taps) {
+          mbar_wait_t(full0 + 8 * s, ph, timed, w_full);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + p.a_bytes;
+          const uint32_t sa = smem0 + (uint32_t)s * (uint32_t)stage_bytes, sb = sa + a_bytes;
           // Descriptors differ only in their 14-bit start-address field, so the loop adds to precomputed 32-bit
           // halves; the 4 K-steps of a 128-byte K-major slab are unrolled (the MMA of a 128xN tile with small N takes
           // only N/2 cycles, so the single issuing thread must not spend more than that per instruction).
           if constexpr (SLAB) {
             // slab mode: every group multiplies the same A slab with its own shifted view of the B patches
             const uint32_t alo = a_lo_base + (sa >> 4);
-            for (int g = 0; g < p.ngroups; ++g) {
+            for (int g = 0; g < ngroups; ++g) {
               const uint32_t blo = b_lo_base + ((sb + (uint32_t)p.grp_b_off[g]) >> 4);
               const uint32_t tg = tacc + (uint32_t)p.grp_acc[g];
               for (int ks = 0; ks < ksteps; ++ks)
                 umma_tf32(tg, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
             }
           } else {
-          for (int t = 0; t < n_taps; ++t) {
-            const uint32_t alo = a_lo_base + ((sa + a_off0 + (uint32_t)tap_off[t]) >> 4);
-            const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[k * n_taps + t] * b_slab : sb + (uint32_t)p.exp_b_off) >> 4);
-            if (ksteps == 4) {
-              umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
-              umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
-              umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
-              umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
-            } else {
-              for (int ks = 0; ks < ksteps; ++ks)
-                umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | t | ks) ? 1u : 0u);
+            for (int t = 0; t < n_taps; ++t) {
+              const uint32_t alo = a_lo_base + ((sa + a_off0 + (uint32_t)tap_off[t]) >> 4);
+              const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[kt + t] * b_slab : sb + b_off) >> 4);
+              if (ksteps == 4) {
+                umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
+                umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
+                umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
+                umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks)
+                  umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | t | ks) ? 1u : 0u);
+              }
             }
           }
-          }
           umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+          if (++s == stages) { s = 0; ph ^= 1; }
         }
         umma_commit(tfull0 + 8 * acc);
+        if (++acc == acc_stages) { acc = 0; aph ^= 1; }
+      }
+      if (timed) {
+        p.stats[blockIdx.x * 8 + 1] = w_full;
+        p.stats[blockIdx.x * 8 + 2] = w_tempty;
+        p.stats[blockIdx.x * 8 + 5] = clock64() - t_start;
+        p.stats[blockIdx.x * 8 + 7] = ti;
       }
     }
     __syncwarp();
@@ -320,7 +449,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     // TMA-loaded into the staging buffer two panels ahead, multiplied in place and stored from the same buffer.
     const int grp = warp >> 2, wq = warp & 3;      // epilogue group, TMEM lane quarter
     const int row = wq * 32 + lane;
-    const bool leader = (threadIdx.x & 127) == 0;  // issues this group's TMA traffic
+    // the group's TMA traffic is issued by the elected lane of its first warp (elect.sync picks the same lane every time,
+    // so bulk-group waits see the stores that lane committed)
+    auto leader = [&]() -> bool { return wq == 0 && elect_one(); };
     const int n_panels = (p.bn + 31) >> 5;
     const bool swz = p.d_row_bytes == 128;
     const bool masked = p.epilogue == EPI_MASK && p.bits_in == nullptr;  // TMA-loaded mask tiles
@@ -329,7 +460,6 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const int nbuf = two_groups ? 1 : p.nbuf;
     uint8_t* const my_staging = staging + (two_groups ? grp * 16384 : 0);
     const int tile_step = two_groups ? 2 * (int)gridDim.x : (int)gridDim.x;
-    const int ti_step = two_groups ? 2 : 1;
     const bool active = two_groups || grp == 0;
     const int r0 = row % p.row_box[0], r1 = (row / p.row_box[0]) % p.row_box[1], r2 = row / (p.row_box[0] * p.row_box[1]);
     int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (group leader only; single-group mode)
@@ -339,8 +469,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         const int col = n_tile * p.bn + q * 32;
 #pragma unroll
         for (int d = 0; d < 5; ++d) c[d] = base[d];
-        c[0] = p.d.off[0] + col % p.cols_per_map;
-        return col / p.cols_per_map;
+        c[0] = p.d.off[0] + (col & (p.cols_per_map - 1));   // cols_per_map is a power of two (host-checked)
+        return col >> p.cpm_shift;
       }
       if constexpr (SLAB) {
 #pragma unroll
@@ -364,16 +494,21 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       ++pf_count;
       if (++pf_q == n_panels) { pf_q = 0; pf_tile += gridDim.x; }
     };
-    if (masked && leader && active) {
+    if (masked && active && leader()) {
       for (int i = 0; i < nbuf - 2; ++i) prefetch_one();  // mask prefetch distance = nbuf - 2 panels
     }
-    int pc = 0;
-    for (int tile = blockIdx.x + (two_groups ? grp * (int)gridDim.x : 0), ti = two_groups ? grp : 0; active && tile < total_tiles;
-         tile += tile_step, ti += ti_step) {
+    int pc = 0, bi = 0;            // panels done so far, staging buffer of the current panel (pc % nbuf without the division)
+    uint32_t bph = 0;              // (pc / nbuf) & 1
+    long long w_tfull = 0;
+    const long long t_epi0 = timed ? clock64() : 0;
+    TileWalk w;
+    walk_init(w, p, active ? (int)blockIdx.x + (two_groups ? grp * (int)gridDim.x : 0) : total_tiles, tile_step);
+    int acc = two_groups ? grp : 0;   // accumulator stage drained by this group for the current tile, and its phase
+    uint32_t aph = 0;
+    for (; w.tile < total_tiles; walk_next(w)) {
       int src[kSrc], n_tile, cd[5];
-      decode_tile(p, tile, src, n_tile);
+      walk_src(w, p, src, n_tile);
       tile_coords(p.d, src, cd);
-      const int acc = ti % acc_stages;
       // element offset (in the tensor the bitmask describes) of this thread's row in panel q, or -1 if the row is clipped
       auto bit_word = [&](int q) -> long {
         int cq[5];
@@ -393,12 +528,12 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           }
         }
       }
-      mbar_wait(tfull0 + 8 * acc, (ti / acc_stages) & 1);
+      mbar_wait_t(tfull0 + 8 * acc, aph, timed, w_tfull);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int q = 0; q < n_panels; ++q, ++pc) {
-        uint8_t* buf = my_staging + (pc % nbuf) * 16384;
-        if (leader) {
+        uint8_t* buf = my_staging + bi * 16384;
+        if (leader()) {
           if (two_groups) {
             tma_wait_read<0>();             // this group's previous store has drained its (single) staging buffer
           } else {
@@ -449,7 +584,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
         const int nchunk = p.d_row_bytes >> 4;
         if (masked) {
-          mbar_wait(aux0 + 8 * (pc % nbuf), (pc / nbuf) & 1);
+          mbar_wait(aux0 + 8 * bi, bph);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < nchunk) {
@@ -473,15 +608,22 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         }
         fence_async_smem();
         epi_bar_sync(grp);
-        if (leader) {
+        if (leader()) {
           int cq[5];
           const int mi = out_panel(cd, n_tile, q, cq);
           tma_store_5d(&p.mapD[mi], smem_u32(buf), cq);
           tma_commit();
         }
+        if (++bi == nbuf) { bi = 0; bph ^= 1; }
       }
+      if (two_groups) aph ^= 1;                                   // this group's stage is used by every other tile
+      else if (++acc == acc_stages) { acc = 0; aph ^= 1; }
     }
-    if (leader) tma_wait_read<0>();
+    if (leader()) tma_wait_read<0>();
+    if (timed && leader()) {
+      p.stats[blockIdx.x * 8 + 3 + grp] = w_tfull;
+      if (grp == 0) p.stats[blockIdx.x * 8 + 6] = clock64() - t_epi0;
+    }
   }
   tc_fence_before();
   __syncthreads();
