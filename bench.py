@@ -343,16 +343,73 @@ def run_b200(args):
     h2d = sum(v.numel() * 4 for v in host.values()) + sum(t.numel() * 4 for b in loader for t in b)
     result_host = torch.empty(T, N, 1, dtype=torch.float32, pin_memory=True)
 
+    # Double-buffered upload: rollout i+1 is copied from pinned host memory into a second obs buffer while update i
+    # runs.  Host->device transfers share one DMA queue with the expert-batch prefetch of Discriminator.update, so the
+    # rollout copy is enqueued (one async copy on its own stream) when the discriminator epochs are over and overlaps
+    # predict_reward + GAE + PPO.update, whose inputs are all on the device.  This is how the storage is fed in the
+    # reference flow too - insert() copies one time slice per env step while the simulator runs (tools/learn.py:111-133).
+    # Every timed step issues and completes one full rollout upload; the small tensors go on the compute stream.
+    up_stream = torch.cuda.Stream(device=dev)
+    try:
+        obs_bufs = [ro.obs, torch.empty_like(ro.obs)]
+        double = True
+    except RuntimeError:                                   # no room for a second obs buffer: upload, then update
+        obs_bufs = [ro.obs, ro.obs]
+        double = False
+    small = [k for k in names if k != "obs"]
+    uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0}
+
+    def enqueue_upload(j):
+        up_stream.wait_stream(torch.cuda.current_stream())  # (serial mode: the buffer is the live one)
+        with torch.cuda.stream(up_stream):
+            obs_bufs[j].copy_(host["obs"], non_blocking=True)
+            uploaded[j].record(up_stream)
+
+    rewards_orig = disc.predict_rewards_rollout
+
+    def rewards_hook(rollouts):
+        if double:
+            enqueue_upload((state["i"] + 1) % 2)
+        return rewards_orig(rollouts)
+
     def step_e2e():
-        for k in names:
+        i = state["i"]
+        if not double:
+            enqueue_upload(0)
+        torch.cuda.current_stream().wait_event(uploaded[i % 2])   # rollout i is resident in obs_bufs[i % 2]
+        ro.obs = obs_bufs[i % 2]
+        for k in small:
             getattr(ro, k).copy_(host[k], non_blocking=True)
         out = step()                                      # tuples are read back inside (one D2H per update call)
         result_host.copy_(ro.returns[:-1], non_blocking=True)   # the step's result tensor back to the host
         torch.cuda.current_stream().synchronize()
+        state["i"] = i + 1
         return out
 
+    def timed_e2e(k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            step_e2e()
+        torch.cuda.current_stream().wait_stream(up_stream)   # the k-th upload finishes inside the timed region
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    disc.predict_rewards_rollout = rewards_hook
+    if double:
+        enqueue_upload(0)
     step_e2e()
-    dt_e2e = timed(step_e2e, args.steps)
+    dt_e2e = timed_e2e(args.steps)
+    torch.cuda.synchronize()
+    disc.predict_rewards_rollout = rewards_orig
+    ro.obs = obs_bufs[0]
+    del obs_bufs[1:]
     e2e = env_steps * args.steps / dt_e2e
     d2h = result_host.numel() * 4 + 8 * 15
 
@@ -381,7 +438,9 @@ def run_b200(args):
                            "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % (ro.obs.numel() * 4 / 1e9),
                            "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce"},
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                        "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned},
+                        "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned,
+                        "upload": ("double-buffered" if double else "serial") + ": rollout i+1 is copied from pinned host memory behind "
+                                  "predict_reward + PPO.update of step i; one full rollout upload + all expert batches per timed step"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu,
                 "other_kernels_seconds": prof.other_summary}
         print(json.dumps(line), flush=True)

@@ -48,7 +48,7 @@ _SIGNATURES = {
     "gc_colsum": [_P, _L, _L, _I, _P, _P],
     "gc_splitk_reduce": [_P, _I, _L, _I, _L, _P, _P, _L, _P, _L, _I, _F, _P],
     "gc_prep_conv_weight": [_P, _P, _P, _I, _I, _I, _P],
-    "gc_unprep_conv_wgrad": [_P, _I, _P, _I, _I, _I, _P],
+    "gc_unprep_conv_wgrad": [_P, _I, _P, _P, _I, _I, _I, _P],
     "gc_prep_fc1_weight": [_P, _P, _I, _I, _L, _P],
     "gc_unprep_fc1_wgrad": [_P, _I, _P, _I, _I, _L, _P],
     "gc_grad_sumsq": [_P, _L, _P, _P],
@@ -212,8 +212,8 @@ def prep_conv_weight(w, w_fprop, w_dgrad, Cout, Cin, layer1):
     call("gc_prep_conv_weight", _ptr(w), _ptr(w_fprop), _ptr(w_dgrad), Cout, Cin, int(layer1), _stream())
 
 
-def unprep_conv_wgrad(part, splits, dw, Cout, Cin, layer1):
-    call("gc_unprep_conv_wgrad", _ptr(part), splits, _ptr(dw), Cout, Cin, int(layer1), _stream())
+def unprep_conv_wgrad(part, splits, dw, Cout, Cin, layer1, dbias=None):
+    call("gc_unprep_conv_wgrad", _ptr(part), splits, _ptr(dw), _ptr(dbias), Cout, Cin, int(layer1), _stream())
 
 
 def prep_fc1_weight(w, w_gemm, out, tail, ld):

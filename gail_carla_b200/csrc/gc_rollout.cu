@@ -211,6 +211,57 @@ __device__ __forceinline__ HeadTail head_tail(const float4 h, const float a0, co
   return o;
 }
 
+// one sample of the fused head tail + PPO / BC loss: returns d loss / d head row, adds this sample's loss terms to part[]
+struct PpoConsts {
+  float ls0, ls1, clip, vcoef, w_act, inv_B, mean, inv;
+  int activation, mode;
+};
+__device__ __forceinline__ float4 ppo_sample(const PpoConsts& c, const float4 h, const float2 a, const float olp, const float vo,
+                                             const float R, const float adv_or_nan, const bool has_adv, double (&part)[3],
+                                             float& out_v, float& out_lp) {
+  const HeadTail t = head_tail(h, a.x, a.y, c.ls0, c.ls1, c.activation);
+  out_v = t.v;
+  out_lp = t.logp;
+  float dlogp = 0.f, dv = 0.f;
+  if (c.mode == 0) {
+    const float A = has_adv ? adv_or_nan : ((R - vo) - c.mean) * c.inv;
+    const float ratio = expf(t.logp - olp);
+    const float lo = 1.f - c.clip, hi = 1.f + c.clip;
+    const float rc = fminf(fmaxf(ratio, lo), hi);
+    const float sa = ratio * A, sb = rc * A;
+    const float in_rng = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+    float dr;  // d min(sa,sb) / d ratio
+    if (sa < sb) dr = A;
+    else if (sa > sb) dr = A * in_rng;
+    else dr = A * (0.5f + 0.5f * in_rng);
+    dlogp = -c.w_act * c.inv_B * dr * ratio;
+    part[1] += (double)(-fminf(sa, sb));
+    // clipped value loss
+    const float dvv = t.v - vo;
+    const float vc = vo + fminf(fmaxf(dvv, -c.clip), c.clip);
+    const float l1 = (t.v - R) * (t.v - R), l2 = (vc - R) * (vc - R);
+    const float vin = (dvv >= -c.clip && dvv <= c.clip) ? 1.f : 0.f;
+    float g;  // d max(l1,l2) / d v
+    if (l1 > l2) g = 2.f * (t.v - R);
+    else if (l1 < l2) g = 2.f * (vc - R) * vin;
+    else g = (t.v - R) + (vc - R) * vin;
+    dv = c.vcoef * 0.5f * c.inv_B * g;
+    part[0] += (double)(0.5f * fmaxf(l1, l2));
+  } else if (c.mode == 1) {
+    dlogp = -c.w_act * c.inv_B;
+    part[2] += (double)(-t.logp);
+  }
+  float4 g4;
+  g4.x = dv;
+  g4.y = dlogp * t.dmu0 * (c.activation ? (1.f - t.mu0 * t.mu0) : 1.f);
+  g4.z = dlogp * t.dmu1 * (c.activation ? (t.mu1 * (1.f - t.mu1)) : 1.f);
+  g4.w = 0.f;
+  return g4;
+}
+
+// Each thread owns 4 consecutive samples: the five per-sample scalar streams are read as one 16-byte load each and the
+// head / action / gradient rows as 4 + 2 + 4 of them, i.e. 13 x 128-bit requests per 4 samples instead of 28 narrower
+// ones (the kernel is a pure 52 B/sample stream; request count and bytes in flight are what bound it).
 __global__ void __launch_bounds__(256) ppo_loss_kernel(const float4* __restrict__ head, const float2* __restrict__ action,
                                                        const float* __restrict__ old_logp, const float* __restrict__ v_old,
                                                        const float* __restrict__ ret, const float* __restrict__ adv_in,
@@ -219,53 +270,38 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float4* __restrict_
                                                        double* __restrict__ acc, int B, float ls0, float ls1, int activation,
                                                        float clip, float vcoef, float w_act, float inv_B, int mode) {
   __shared__ double red[32 * 3];
-  float mean = 0.f, inv = 1.f;
-  if (mode == 0 && adv_in == nullptr) adv_moments(stats, mean, inv);
+  PpoConsts c{ls0, ls1, clip, vcoef, w_act, inv_B, 0.f, 1.f, activation, mode};
+  if (mode == 0 && adv_in == nullptr) adv_moments(stats, c.mean, c.inv);
   double part[3] = {0.0, 0.0, 0.0};
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
-    const float4 h = head[b];
-    const float2 a = action[b];
-    const HeadTail t = head_tail(h, a.x, a.y, ls0, ls1, activation);
-    if (out_value) out_value[b] = t.v;
-    if (out_logp) out_logp[b] = t.logp;
-    float dlogp = 0.f, dv = 0.f;
-    if (mode == 0) {
-      const float A = adv_in ? adv_in[b] : ((ret[b] - v_old[b]) - mean) * inv;
-      const float ratio = expf(t.logp - old_logp[b]);
-      const float lo = 1.f - clip, hi = 1.f + clip;
-      const float rc = fminf(fmaxf(ratio, lo), hi);
-      const float sa = ratio * A, sb = rc * A;
-      const float in_rng = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-      float dr;  // d min(sa,sb) / d ratio
-      if (sa < sb) dr = A;
-      else if (sa > sb) dr = A * in_rng;
-      else dr = A * (0.5f + 0.5f * in_rng);
-      dlogp = -w_act * inv_B * dr * ratio;
-      part[1] += (double)(-fminf(sa, sb));
-      // clipped value loss
-      const float R = ret[b], vo = v_old[b];
-      const float dvv = t.v - vo;
-      const float vc = vo + fminf(fmaxf(dvv, -clip), clip);
-      const float l1 = (t.v - R) * (t.v - R), l2 = (vc - R) * (vc - R);
-      const float vin = (dvv >= -clip && dvv <= clip) ? 1.f : 0.f;
-      float g;  // d max(l1,l2) / d v
-      if (l1 > l2) g = 2.f * (t.v - R);
-      else if (l1 < l2) g = 2.f * (vc - R) * vin;
-      else g = (t.v - R) + (vc - R) * vin;
-      dv = vcoef * 0.5f * inv_B * g;
-      part[0] += (double)(0.5f * fmaxf(l1, l2));
-    } else if (mode == 1) {
-      dlogp = -w_act * inv_B;
-      part[2] += (double)(-t.logp);
-    }
+  const bool has_adv = adv_in != nullptr;
+  const int B4 = B >> 2;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B4; i += gridDim.x * blockDim.x) {
+    const float4 h0 = head[4 * i], h1 = head[4 * i + 1], h2 = head[4 * i + 2], h3 = head[4 * i + 3];
+    const float4 a01 = reinterpret_cast<const float4*>(action)[2 * i], a23 = reinterpret_cast<const float4*>(action)[2 * i + 1];
+    const float4 olp = mode == 0 ? reinterpret_cast<const float4*>(old_logp)[i] : z4;
+    const float4 vo = mode == 0 ? reinterpret_cast<const float4*>(v_old)[i] : z4;
+    const float4 R = mode == 0 ? reinterpret_cast<const float4*>(ret)[i] : z4;
+    const float4 ad = (mode == 0 && has_adv) ? reinterpret_cast<const float4*>(adv_in)[i] : z4;
+    float4 ov, ol;
+    const float4 g0 = ppo_sample(c, h0, make_float2(a01.x, a01.y), olp.x, vo.x, R.x, ad.x, has_adv, part, ov.x, ol.x);
+    const float4 g1 = ppo_sample(c, h1, make_float2(a01.z, a01.w), olp.y, vo.y, R.y, ad.y, has_adv, part, ov.y, ol.y);
+    const float4 g2 = ppo_sample(c, h2, make_float2(a23.x, a23.y), olp.z, vo.z, R.z, ad.z, has_adv, part, ov.z, ol.z);
+    const float4 g3 = ppo_sample(c, h3, make_float2(a23.z, a23.w), olp.w, vo.w, R.w, ad.w, has_adv, part, ov.w, ol.w);
+    if (out_value) reinterpret_cast<float4*>(out_value)[i] = ov;
+    if (out_logp) reinterpret_cast<float4*>(out_logp)[i] = ol;
     if (mode != 2) {
-      float4 g4;
-      g4.x = dv;
-      g4.y = dlogp * t.dmu0 * (activation ? (1.f - t.mu0 * t.mu0) : 1.f);
-      g4.z = dlogp * t.dmu1 * (activation ? (t.mu1 * (1.f - t.mu1)) : 1.f);
-      g4.w = 0.f;
-      d_head[b] = g4;
+      d_head[4 * i] = g0; d_head[4 * i + 1] = g1; d_head[4 * i + 2] = g2; d_head[4 * i + 3] = g3;
     }
+  }
+  // ragged tail (B % 4 samples), one thread each
+  for (int b = 4 * B4 + blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    float ov, ol;
+    const float4 g = ppo_sample(c, head[b], action[b], mode == 0 ? old_logp[b] : 0.f, mode == 0 ? v_old[b] : 0.f,
+                                mode == 0 ? ret[b] : 0.f, (mode == 0 && has_adv) ? adv_in[b] : 0.f, has_adv, part, ov, ol);
+    if (out_value) out_value[b] = ov;
+    if (out_logp) out_logp[b] = ol;
+    if (mode != 2) d_head[b] = g;
   }
   if (acc && mode != 2) {
     gc::block_sum<3>(part, red);
@@ -405,7 +441,12 @@ int gc_ppo_loss_fwd_bwd(const float* head_out, const float* actions, const float
   if (mode == 0) GC_REQUIRE(old_logp && value_old && returns && (adv || adv_stats) && d_head_out,
                             "gc_ppo_loss_fwd_bwd: PPO mode needs old_logp, value_old, returns, adv|adv_stats, d_head_out");
   if (mode == 1) GC_REQUIRE(d_head_out, "gc_ppo_loss_fwd_bwd: BC mode needs d_head_out");
-  const int grid = std::min((B + 255) / 256, 16 * gc::kNumSMs);
+  // the 128-bit path needs 16-byte aligned per-sample streams (torch allocations are; sliced views may not be)
+  auto al16 = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
+  GC_REQUIRE(al16(head_out) && al16(actions) && al16(old_logp) && al16(value_old) && al16(returns) && al16(adv) &&
+                 al16(d_head_out) && al16(out_value) && al16(out_logp),
+             "gc_ppo_loss_fwd_bwd: per-sample arrays must be 16-byte aligned");
+  const int grid = std::min((B / 4 + 255) / 256 + 1, 8 * gc::kNumSMs);
   ppo_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)head_out, (const float2*)actions, old_logp, value_old, returns, adv, adv_stats, (float4*)d_head_out,
       out_value, out_logp, loss_acc, B, logstd0, logstd1, activation, clip, value_coef, action_weight, 1.0f / (float)B, mode);

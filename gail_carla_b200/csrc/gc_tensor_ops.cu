@@ -38,11 +38,11 @@ __global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const float* __rest
   }
   __syncthreads();
   float4* o = reinterpret_cast<float4*>(out + ((long)b * kS2dH + Y0) * (kS2dW * kS2dC));
-  for (int i = threadIdx.x; i < kGatherRows * kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,0) of one (Y,X,dy,dx)
+  for (int i = threadIdx.x; i < kGatherRows * kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,1) of one (Y,X,dy,dx)
     const int yy = i / (kS2dW * 4), j = i % (kS2dW * 4);
     const int X = j >> 2, dy = (j >> 1) & 1, dx = j & 1;
     const int x = 2 * X + dx;
-    o[i] = make_float4(tile[yy][0][dy][x], tile[yy][1][dy][x], tile[yy][2][dy][x], 0.f);
+    o[i] = make_float4(tile[yy][0][dy][x], tile[yy][1][dy][x], tile[yy][2][dy][x], 1.f);  // pad channel = 1: conv1 bias-grad column
   }
 }
 
@@ -306,8 +306,13 @@ __global__ void unprep_conv_kernel(const float* __restrict__ part, int splits, f
   for (int z = 0; z < splits; ++z) s += part[(long)z * total + src];
   dw[i] = s;
 }
-__global__ void unprep_conv1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw) {
+__global__ void unprep_conv1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw, float* __restrict__ dbias) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dw[n][c][ky][kx], 32*3*16
+  if (i < 32 && dbias) {  // pad channel (q = 3) of tap (0,0): sum over pixels of dy[n] * 1.0 = bias gradient
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[z * (32 * 64) + i * 64 + 3];
+    dbias[i] = s;
+  }
   if (i >= 32 * 48) return;
   const int kx = i & 3, ky = (i >> 2) & 3, c = (i >> 4) % 3, n = (i >> 4) / 3;
   const int ky2 = ky >> 1, dy = ky & 1, px = kx >> 1, dx = kx & 1;
@@ -517,13 +522,14 @@ int gc_prep_conv_weight(const float* w, float* w_fprop, float* w_dgrad, int Cout
   return gc::launch_status("prep_conv_kernel");
 }
 
-int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, int Cout, int Cin, int layer1, void* stream) {
+int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, float* dbias, int Cout, int Cin, int layer1, void* stream) {
   GC_REQUIRE(part && dw && splits >= 1, "gc_unprep_conv_wgrad: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (layer1) {
     GC_REQUIRE(Cout == 32 && Cin == 3, "gc_unprep_conv_wgrad: layer1 expects 32x3x4x4");
-    unprep_conv1_kernel<<<6, 256, 0, st>>>(part, splits, dw);
+    unprep_conv1_kernel<<<6, 256, 0, st>>>(part, splits, dw, dbias);
   } else {
+    GC_REQUIRE(dbias == nullptr, "gc_unprep_conv_wgrad: the bias-gradient column exists only for layer 1");
     const long n = (long)Cout * Cin * 16;
     unprep_conv_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, splits, dw, Cout, Cin);
   }

@@ -130,7 +130,9 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GC_REQUIRE(p.bn % 16 == 0 && p.bn >= 16 && (p.bn <= 256 || p.ngroups > 0), "%s: tile N %d not a multiple of 16 in [16,256]", what, p.bn);
   GC_REQUIRE(p.bk % 8 == 0 && p.bk >= 8, "%s: bk %d not a multiple of 8", what, p.bk);
   if (!pl.a_mn || !pl.b_mn) GC_REQUIRE(p.bk == 32, "%s: K-major operands need bk == 32 (got %d)", what, p.bk);
-  if (p.a_bytes == 0) p.a_bytes = pl.a_mn ? 4 * p.bk * 128 : 16384;
+  // MN-major A: only the panels that exist are staged (Cout = 32 -> 1 of the 4 panels an M = 128 MMA reads; the other
+  // three read whatever follows in shared memory into accumulator rows that are never stored)
+  if (p.a_bytes == 0) p.a_bytes = pl.a_mn ? ((p.a_panels * p.bk * 128 + 1023) & ~1023) : 16384;
   if (p.taps == 0) p.taps = 1;
   if (p.row_box[0] == 0) { p.row_box[0] = 128; p.row_box[1] = 1; p.row_box[2] = 1; }
   const int bpan = (p.bn + 31) / 32;
@@ -146,6 +148,12 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   }
   const int resident = p.b_slabs * p.b_slab_bytes;
   p.nbuf = (p.epilogue == EPI_MASK && p.bits_in == nullptr) ? (p.b_resident ? 3 : 4) : 2;
+  if (p.nbuf == 2) {
+    // two staging buffers per epilogue group (the TMA store of panel i drains while panel i+1 is formed) when that still
+    // leaves a deep operand ring - in practice the small-tile streaming layers (conv1), whose epilogue is the bottleneck
+    const int stage_b = p.a_bytes + p.b_bytes;
+    if ((kSmemBudget - (4 * 16384 + 4096 + resident)) / stage_b >= 6) p.nbuf = 4;
+  }
   if (p.acc_stages == 0) p.acc_stages = 2;
   p.tmem_cols = pow2_cols(p.acc_stages * bpan * 32);
   GC_REQUIRE(p.tmem_cols <= 512, "%s: accumulators need %d TMEM columns", what, p.tmem_cols);
@@ -177,20 +185,22 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     static long long* d_stats = nullptr;   // debug only: GC_UMMA_STATS=1 prints where each role of the kernel waits
     static const bool want_stats = getenv("GC_UMMA_STATS") != nullptr;
     if (want_stats) {
-      if (!d_stats) cudaMalloc(&d_stats, gc::kNumSMs * 8 * sizeof(long long));
-      cudaMemsetAsync(d_stats, 0, gc::kNumSMs * 8 * sizeof(long long), st);
+      if (!d_stats) cudaMalloc(&d_stats, gc::kNumSMs * 16 * sizeof(long long));
+      cudaMemsetAsync(d_stats, 0, gc::kNumSMs * 16 * sizeof(long long), st);
       p.stats = d_stats;
     }
     kern<<<grid, 320, smem, st>>>(p);
     if (want_stats) {
-      long long h[gc::kNumSMs * 8];
+      long long h[gc::kNumSMs * 16];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
-      double m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (unsigned c = 0; c < grid.x; ++c) for (int i = 0; i < 8; ++i) m[i] += (double)h[c * 8 + i] / grid.x;
+      double m[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (unsigned c = 0; c < grid.x; ++c) for (int i = 0; i < 16; ++i) m[i] += (double)h[c * 16 + i] / grid.x;
       fprintf(stderr, "[umma-stats] %-26s ctas=%u tiles/cta=%.1f k_iters=%d bn=%d stages=%d | clocks/cta total=%.0f prod_wait_empty=%.0f "
-                      "mma_wait_full=%.0f mma_wait_tmem=%.0f epi0_wait_acc=%.0f epi1_wait_acc=%.0f epi0_total=%.0f\n",
-              what, grid.x, m[7], p.k_iters, p.bn, p.stages, m[5], m[0], m[1], m[2], m[3], m[4], m[6]);
+                      "mma_wait_full=%.0f mma_wait_tmem=%.0f epi0_wait_acc=%.0f epi1_wait_acc=%.0f epi0_total=%.0f | epi0 per panel (%.0f panels): free=%.0f ld=%.0f "
+                      "math=%.0f sts+fence=%.0f bar=%.0f store=%.0f nbuf=%d\n",
+              what, grid.x, m[7], p.k_iters, p.bn, p.stages, m[5], m[0], m[1], m[2], m[3], m[4], m[6], m[12],
+              m[8] / std::max(1.0, m[12]), m[9] / std::max(1.0, m[12]), m[10] / std::max(1.0, m[12]), m[13] / std::max(1.0, m[12]), m[14] / std::max(1.0, m[12]), m[11] / std::max(1.0, m[12]), p.nbuf);
     }
     return gc::launch_status(what);
   };

@@ -117,6 +117,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// explicit shared-memory accesses with 32-bit addresses: through a generic pointer the compiler emits generic ST.E/LD.E
+// with 64-bit address arithmetic for every 16-byte chunk (profiles/r01_ncu_conv1_fprop_source.txt)
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint64_t mk64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 __device__ __forceinline__ void coords(const TmaAddr& t, const int (&src)[kSrc], int lo, int hi, int (&c)[5]) {
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
-      if (timed) p.stats[blockIdx.x * 8 + 0] = w_empty;
+      if (timed) p.stats[blockIdx.x * 16 + 0] = w_empty;
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -435,10 +446,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         if (++acc == acc_stages) { acc = 0; aph ^= 1; }
       }
       if (timed) {
-        p.stats[blockIdx.x * 8 + 1] = w_full;
-        p.stats[blockIdx.x * 8 + 2] = w_tempty;
-        p.stats[blockIdx.x * 8 + 5] = clock64() - t_start;
-        p.stats[blockIdx.x * 8 + 7] = ti;
+        p.stats[blockIdx.x * 16 + 1] = w_full;
+        p.stats[blockIdx.x * 16 + 2] = w_tempty;
+        p.stats[blockIdx.x * 16 + 5] = clock64() - t_start;
+        p.stats[blockIdx.x * 16 + 7] = ti;
       }
     }
     __syncwarp();
@@ -456,9 +467,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const bool swz = p.d_row_bytes == 128;
     const bool masked = p.epilogue == EPI_MASK && p.bits_in == nullptr;  // TMA-loaded mask tiles
     const bool bitmask = p.epilogue == EPI_MASK && p.bits_in != nullptr;
-    const bool two_groups = !masked && acc_stages == 2;  // ping-pong on the two accumulator stages, one staging buffer each
-    const int nbuf = two_groups ? 1 : p.nbuf;
-    uint8_t* const my_staging = staging + (two_groups ? grp * 16384 : 0);
+    const bool two_groups = !masked && acc_stages == 2;  // ping-pong on the two accumulator stages, nbuf/2 staging buffers each
+    const int nbuf = two_groups ? (p.nbuf >> 1) : p.nbuf;
+    uint8_t* const my_staging = staging + (two_groups ? grp * nbuf * 16384 : 0);
     const int tile_step = two_groups ? 2 * (int)gridDim.x : (int)gridDim.x;
     const bool active = two_groups || grp == 0;
     const int r0 = row % p.row_box[0], r1 = (row / p.row_box[0]) % p.row_box[1], r2 = row / (p.row_box[0] * p.row_box[1]);
@@ -497,9 +508,28 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     if (masked && active && leader()) {
       for (int i = 0; i < nbuf - 2; ++i) prefetch_one();  // mask prefetch distance = nbuf - 2 panels
     }
+    // this thread's eight 16-byte chunk offsets inside a staging buffer (row-major rows of d_row_bytes, 128-byte rows
+    // XOR-swizzled like the TMA box), computed once
+    const int nchunk = p.d_row_bytes >> 4;
+    uint32_t soff[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t o = (uint32_t)row * (uint32_t)p.d_row_bytes + j * 16;
+      if (swz) o ^= ((o >> 7) & 7) << 4;
+      soff[j] = o;
+    }
+    const long bs0 = p.bit_str[0], bs1 = p.bit_str[1], bs2 = p.bit_str[2], bbase0 = p.bit_base[0];
+    const long thread_bit_off = r0 * bs0 + r1 * bs1 + r2 * bs2;
+    const int ext0[3] = {p.row_ext[0][0], p.row_ext[0][1], p.row_ext[0][2]};
+    const bool r2_ok = r2 < p.row_box[2];
+    const int epi = p.epilogue;
+    const float slope = p.slope;
+    const bool bias_smem = p.nt * p.bn <= 512;
+    const bool want_bits = p.bits_out != nullptr && epi == EPI_BIAS_LRELU;
+    const uint32_t s_bias_u32 = smem_u32(s_bias), my_staging_u32 = smem_u32(my_staging);
     int pc = 0, bi = 0;            // panels done so far, staging buffer of the current panel (pc % nbuf without the division)
     uint32_t bph = 0;              // (pc / nbuf) & 1
-    long long w_tfull = 0;
+    long long w_tfull = 0, e_free = 0, e_ld = 0, e_math = 0, e_store = 0, e_sts = 0, e_bar = 0;
     const long long t_epi0 = timed ? clock64() : 0;
     TileWalk w;
     walk_init(w, p, active ? (int)blockIdx.x + (two_groups ? grp * (int)gridDim.x : 0) : total_tiles, tile_step);
@@ -509,13 +539,17 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       int src[kSrc], n_tile, cd[5];
       walk_src(w, p, src, n_tile);
       tile_coords(p.d, src, cd);
-      // element offset (in the tensor the bitmask describes) of this thread's row in panel q, or -1 if the row is clipped
+      // 32-bit word (in the bit tensor of the activation the mask describes) of this thread's row in panel q, or -1 if the
+      // row is clipped.  Strides / extents of map 0 live in registers (hoisted above the tile loop).
       auto bit_word = [&](int q) -> long {
         int cq[5];
         const int mi = out_panel(cd, n_tile, q, cq);
         const int c1 = cq[1] + r0, c2 = cq[2] + r1, c3 = cq[3] + r2;
-        if (r2 >= p.row_box[2] || c1 >= p.row_ext[mi][0] || c2 >= p.row_ext[mi][1] || c3 >= p.row_ext[mi][2]) return -1;
-        return (p.bit_base[mi] + c1 * p.bit_str[0] + c2 * p.bit_str[1] + c3 * p.bit_str[2] + cq[0]) >> 5;
+        const int x0 = mi == 0 ? ext0[0] : p.row_ext[mi][0], x1 = mi == 0 ? ext0[1] : p.row_ext[mi][1],
+                  x2 = mi == 0 ? ext0[2] : p.row_ext[mi][2];
+        if (!r2_ok || c1 >= x0 || c2 >= x1 || c3 >= x2) return -1;
+        const long base = mi == 0 ? bbase0 : p.bit_base[mi];
+        return (base + cq[1] * bs0 + cq[2] * bs1 + cq[3] * bs2 + cq[0] + thread_bit_off) >> 5;
       };
       unsigned mbits[8];
       if (bitmask) {  // issued before waiting for the accumulator: the loads overlap the tile's mainloop
@@ -532,88 +566,94 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int q = 0; q < n_panels; ++q, ++pc) {
-        uint8_t* buf = my_staging + bi * 16384;
+        const uint32_t buf = my_staging_u32 + (uint32_t)bi * 16384u;
+        int cq_st[5];   // store coordinates of this panel, formed before the barriers so the leader only has to issue
+        const int mi_st = out_panel(cd, n_tile, q, cq_st);
+        const long long c0 = timed ? clock64() : 0;
         if (leader()) {
           if (two_groups) {
-            tma_wait_read<0>();             // this group's previous store has drained its (single) staging buffer
+            // the store that last used this staging buffer has drained it (ring of nbuf buffers per group)
+            if (nbuf == 1) tma_wait_read<0>();
+            else tma_wait_read<1>();
           } else {
             if (pc >= 2) tma_wait_read<1>();  // the store of panel pc-2 has drained its staging buffer
             if (masked) prefetch_one();       // panel pc+nbuf-2 -> the buffer the store of panel pc-2 just released
           }
         }
         epi_bar_sync(grp);
+        const long long c1 = timed ? clock64() : 0;
         float v[32];
         tmem_ld32(tacc + (uint32_t)(q * 32), v);
+        const long long c2 = timed ? clock64() : 0;
         if (q == n_panels - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
         }
         const int col0 = n_tile * p.bn + q * 32;
-        if (p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) {
-          if (p.nt * p.bn <= 512) {  // bias staged in shared memory: 8 broadcast LDS.128 instead of 32 global loads
-            const float4* sb4 = reinterpret_cast<const float4*>(s_bias + col0);
+        unsigned bits_w = 0u;
+        long bits_wi = -1;
+        if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) {
+          if (bias_smem) {  // bias staged in shared memory: 8 broadcast LDS.128 instead of 32 global loads
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = sb4[j];
+              const float4 b = lds128(s_bias_u32 + (uint32_t)(col0 + 4 * j) * 4u);
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
           }
-          if (p.epilogue == EPI_BIAS_LRELU) {
+          if (epi == EPI_BIAS_LRELU) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gc::leaky(v[j], p.slope);
+            for (int j = 0; j < 32; ++j) v[j] = gc::leaky(v[j], slope);
           }
         }
-        if (p.bits_out != nullptr && p.epilogue == EPI_BIAS_LRELU) {
-          unsigned w = 0u;
+        if (want_bits) {
+          unsigned w4[4] = {0u, 0u, 0u, 0u};   // four short OR chains instead of one 32-deep dependency chain
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w |= (v[j] > 0.f && col0 + j < p.n_total) ? (1u << j) : 0u;
-          const long wi = bit_word(q);
-          if (wi >= 0) p.bits_out[wi] = w;
+          for (int j = 0; j < 32; ++j) w4[j & 3] |= v[j] > 0.f ? (1u << j) : 0u;
+          unsigned w = (w4[0] | w4[1]) | (w4[2] | w4[3]);
+          if (col0 + 32 > p.n_total) w &= (1u << (p.n_total - col0)) - 1u;   // partial last panel
+          bits_w = w;
+          bits_wi = bit_word(q);
         }
         if (bitmask) {
           unsigned w = 0u;
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) w = (qq == q) ? mbits[qq] : w;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? 1.f : p.slope;
+          for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? 1.f : slope;
         }
-        const uint32_t rbase = (uint32_t)row * (uint32_t)p.d_row_bytes;
-        const int nchunk = p.d_row_bytes >> 4;
         if (masked) {
           mbar_wait(aux0 + 8 * bi, bph);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j < nchunk) {
-              uint32_t o = rbase + j * 16;
-              if (swz) o ^= ((o >> 7) & 7) << 4;
-              const float4 m = *reinterpret_cast<const float4*>(buf + o);
-              v[4 * j + 0] *= m.x > 0.f ? 1.f : p.slope;
-              v[4 * j + 1] *= m.y > 0.f ? 1.f : p.slope;
-              v[4 * j + 2] *= m.z > 0.f ? 1.f : p.slope;
-              v[4 * j + 3] *= m.w > 0.f ? 1.f : p.slope;
+              const float4 m = lds128(buf + soff[j]);
+              v[4 * j + 0] *= m.x > 0.f ? 1.f : slope;
+              v[4 * j + 1] *= m.y > 0.f ? 1.f : slope;
+              v[4 * j + 2] *= m.z > 0.f ? 1.f : slope;
+              v[4 * j + 3] *= m.w > 0.f ? 1.f : slope;
             }
           }
         }
+        const long long c2a = timed ? clock64() : 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (j < nchunk) {
-            uint32_t o = rbase + j * 16;
-            if (swz) o ^= ((o >> 7) & 7) << 4;
-            *reinterpret_cast<float4*>(buf + o) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
+          if (j < nchunk) sts128(buf + soff[j], v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         fence_async_smem();
+        const long long c2b = timed ? clock64() : 0;
         epi_bar_sync(grp);
+        const long long c3 = timed ? clock64() : 0;
+        // the LeakyReLU' bit word goes out after the proxy fence so the fence never waits on a global store
+        if (bits_wi >= 0) p.bits_out[bits_wi] = bits_w;
         if (leader()) {
-          int cq[5];
-          const int mi = out_panel(cd, n_tile, q, cq);
-          tma_store_5d(&p.mapD[mi], smem_u32(buf), cq);
+          tma_store_5d(&p.mapD[mi_st], buf, cq_st);
           tma_commit();
         }
+        if (timed) { e_free += c1 - c0; e_ld += c2 - c1; e_math += c2a - c2; e_sts += c2b - c2a; e_bar += c3 - c2b; e_store += clock64() - c3; }
         if (++bi == nbuf) { bi = 0; bph ^= 1; }
       }
       if (two_groups) aph ^= 1;                                   // this group's stage is used by every other tile
@@ -621,8 +661,17 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     }
     if (leader()) tma_wait_read<0>();
     if (timed && leader()) {
-      p.stats[blockIdx.x * 8 + 3 + grp] = w_tfull;
-      if (grp == 0) p.stats[blockIdx.x * 8 + 6] = clock64() - t_epi0;
+      p.stats[blockIdx.x * 16 + 3 + grp] = w_tfull;
+      if (grp == 0) {
+        p.stats[blockIdx.x * 16 + 6] = clock64() - t_epi0;
+        p.stats[blockIdx.x * 16 + 8] = e_free;    // waiting for a free staging buffer + group barrier
+        p.stats[blockIdx.x * 16 + 9] = e_ld;      // tcgen05.ld + wait::ld
+        p.stats[blockIdx.x * 16 + 10] = e_math;   // bias / activation / bits / st.shared / proxy fence / group barrier
+        p.stats[blockIdx.x * 16 + 11] = e_store;  // TMA store issue
+        p.stats[blockIdx.x * 16 + 12] = pc;       // panels
+        p.stats[blockIdx.x * 16 + 13] = e_sts;    // st.shared + proxy fence
+        p.stats[blockIdx.x * 16 + 14] = e_bar;    // group barrier before the store
+      }
     }
   }
   tc_fence_before();

@@ -233,7 +233,10 @@ class ConvStack:
         A.conv_dgrad(conv_geom(1, B), dA[1][row0:], self.wd[0], dA[0][row0:], None, SLOPE)
 
     def backward_params(self, ws: Workspace, B: int, B_bias: int) -> None:
-        """Weight gradients from (delta_k, a_{k-1}) over rows [0,B); bias gradients over rows [0,B_bias)."""
+        """Weight gradients from (delta_k, a_{k-1}) over rows [0,B); bias gradients over rows [0,B_bias).
+        conv1's bias gradient is a column of its wgrad: the pad channel of the space-to-depth image is 1.0 for image
+        rows and 0.0 for the gradient-penalty rows (u = d gp / d g written by gc_grad_penalty), which are exactly the
+        rows [B_bias, B) that must not contribute - so dY1, the largest gradient tensor, is not re-read."""
         dA = ws.grads()
         for i in range(1, 5):
             g = conv_geom4_compact(B) if i == 4 else conv_geom(i, B)
@@ -241,8 +244,10 @@ class ConvStack:
             n = 2048 if i == 1 else CONV_CH[i] * CONV_CH[i - 1] * 16
             part = ws.partial(f"cw{i}", splits * n)
             A.conv_wgrad(g, dA[i], ws.A[i - 1], part, splits)
-            A.unprep_conv_wgrad(part, splits, self.flat.g(self.wname(i)), CONV_CH[i], CONV_CH[i - 1], i == 1)
-            if B_bias > 0:
+            fused_bias = i == 1 and B_bias > 0
+            A.unprep_conv_wgrad(part, splits, self.flat.g(self.wname(i)), CONV_CH[i], CONV_CH[i - 1], i == 1,
+                                self.flat.g(self.bname(i)) if fused_bias else None)
+            if B_bias > 0 and not fused_bias:
                 rows = B_bias * (96 * 96, 46 * 46, 22 * 22, 100)[i - 1]
                 A.colsum(dA[i], CONV_CH[i], rows, CONV_CH[i], self.flat.g(self.bname(i)))
 

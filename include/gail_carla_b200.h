@@ -125,8 +125,10 @@ int gc_splitk_reduce(const float* part, int splits, long M, int N, long ldp, con
  * [cls=py*2+px][c][a][b'][n] (ky=py+2a, kx=px+2b').  layer1=1 selects the space-to-depth form of conv1:
  * fprop [32][ky2][px][dy][dx][c4] (c=3 zero) and dgrad [16 (dy,dx,c4)][a][b'][n]. */
 int gc_prep_conv_weight(const float* w, float* w_fprop, float* w_dgrad, int Cout, int Cin, int layer1, void* stream);
-/* inverse for gradients: dw[Cout,Cin,4,4] = sum_z part[z][n][ky][kx][c] (same fprop operand layout). */
-int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, int Cout, int Cin, int layer1, void* stream);
+/* inverse for gradients: dw[Cout,Cin,4,4] = sum_z part[z][n][ky][kx][c] (same fprop operand layout).
+ * layer1 with dbias != NULL: the pad channel of the space-to-depth image holds 1.0 (gc_gather_obs_s2d), so the wgrad
+ * column of that channel is sum_pixels dy[n] - the bias gradient - and is written to dbias[Cout] (no column-sum pass). */
+int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, float* dbias, int Cout, int Cin, int layer1, void* stream);
 /* FC1 weight [out, 25600+tail] (NCHW-flatten columns c*100+p) -> [out, ld] with NHWC columns p*256+c, tail copied, pad 0. */
 int gc_prep_fc1_weight(const float* w, float* w_gemm, int out, int tail, long ld, void* stream);
 /* dw[out, 25600+tail] = sum_z part[z][out][ld] with the inverse column permutation. */

@@ -139,7 +139,7 @@ def gather_obs_s2d(src, idx, out, B):
     x = rows[idx[:B]] if idx is not None else rows[:B]
     mean = torch.tensor(NORM_MEAN).view(1, 3, 1, 1); std = torch.tensor(NORM_STD).view(1, 3, 1, 1)
     x = (x - mean) / std
-    x4 = torch.cat([x, torch.zeros(B, 1, 192, 192)], 1)                      # [B,4,192,192]
+    x4 = torch.cat([x, torch.ones(B, 1, 192, 192)], 1)                       # [B,4,192,192], pad channel = 1
     x4 = x4.view(B, 4, 96, 2, 96, 2).permute(0, 2, 4, 3, 5, 1)               # b,Y,X,dy,dx,c
     out.view(-1)[:B * 96 * 96 * 16] = x4.reshape(-1)
 
@@ -262,10 +262,12 @@ def prep_conv_weight(w, w_fprop, w_dgrad, Cout, Cin, layer1):
             w_dgrad.view(-1)[:w.numel()] = t.permute(3, 5, 1, 2, 4, 0).reshape(-1)
 
 
-def unprep_conv_wgrad(part, splits, dw, Cout, Cin, layer1):
+def unprep_conv_wgrad(part, splits, dw, Cout, Cin, layer1, dbias=None):
     if layer1:
         s = part.reshape(-1)[:splits * 2048].view(splits, 32, 2, 2, 2, 2, 4).sum(0)   # n,ky2,px,dy,dx,c
         dw.view(32, 3, 4, 4).copy_(s.permute(0, 5, 1, 3, 2, 4).reshape(32, 4, 4, 4)[:, :3])
+        if dbias is not None:   # pad channel of tap (0,0): sum over pixels of dy[n] * 1.0
+            dbias.view(-1)[:32].copy_(s[:, 0, 0, 0, 0, 3])
     else:
         n = Cout * Cin * 16
         s = part.reshape(-1)[:splits * n].view(splits, Cout, 4, 4, Cin).sum(0)

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out; rm -f gpurun_out/*.ncu-rep
+for L in 1 2; do
+B=4096 LAYER=$L OP=fprop REPS=2 timeout 120 python tests/gpu_probe_one.py > gpurun_out/plain_one.log 2>&1 && \
+B=4096 LAYER=$L OP=fprop REPS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:umma_gemm -s 1 -c 1 -o gpurun_out/r01_conv${L}_fprop_full python tests/gpu_probe_one.py > gpurun_out/ncu_one_$L.log 2>&1
+done
+ls -la gpurun_out/*.ncu-rep

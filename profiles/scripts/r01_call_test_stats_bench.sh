@@ -1,0 +1,8 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t_all.log
+GC_UMMA_STATS=1 B=4096 REPS=1 timeout 300 python tests/gpu_probe_layers.py > gpurun_out/stats_layers3.log 2>&1
+B=4096 REPS=3 timeout 300 python tests/gpu_probe_layers.py 2>&1 | tail -3
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; tail -3 gpurun_out/bench_n1.err
+python -c "
+import json;d=json.load(open('gpurun_out/bench_n1.json'));print(d['ms_per_step'],d['value'],d['e2e'],d['roofline']['achieved'],d['roofline']['share_of_step'])"
+nvidia-smi --query-gpu=memory.used,memory.total --format=csv

@@ -223,7 +223,12 @@ def test_weight_layouts_roundtrip_and_adam():
             wf = torch.zeros(n, device=dev); wd = torch.zeros(n, device=dev)
             mod.prep_conv_weight(w.to(dev), wf, wd, Cout, Cin, l1)
             part = torch.stack([wf, 2 * wf]); dw = torch.zeros(Cout, Cin, 4, 4, device=dev)
-            mod.unprep_conv_wgrad(part, 2, dw, Cout, Cin, l1)
+            if l1:   # the pad-channel column of tap (0,0) carries the bias gradient (pad channel of X0 = 1.0)
+                part = part.clone(); part.view(2, 32, 64)[:, :, 3] = torch.arange(64, dtype=torch.float32, device=dev).view(2, 32)
+            db = torch.zeros(Cout, device=dev)
+            mod.unprep_conv_wgrad(part, 2, dw, Cout, Cin, l1, db if l1 else None)
+            if l1:
+                close(db.cpu(), (torch.arange(32.) + torch.arange(32., 64.)), 0, 0, "conv1 bias-grad column")
             res[tag] = (wf, wd, dw)
         for a_, b_ in zip(res["gpu"], res["ref"]):
             close(a_, b_, 0, 0, "conv layouts")
