@@ -186,8 +186,18 @@ class Profiler:
         e0.record()
         r = self._orig(name, *args)
         e1.record()
-        self.records.append((key, fl, e0, e1))
+        self.records.append((key, fl, e0, e1, self._bytes(name, args)))
         return r
+
+    @staticmethod
+    def _bytes(name, a):
+        """Algorithmic HBM bytes of a conv contraction: each operand read once, the result written once (fp32)."""
+        if name in ("gc_conv_fprop", "gc_conv_dgrad", "gc_conv_wgrad"):
+            g = a[0]._obj
+            x = 4.0 * g.B * g.H * g.W * g.Cin
+            y = 4.0 * g.B * g.OH * g.OW * g.Cout
+            return x + y          # fprop: read x, write y | dgrad: read dy, write dx | wgrad: read dy and x (dw is tiny)
+        return 0.0
 
     @staticmethod
     def _flops(name, a):
@@ -205,10 +215,10 @@ class Profiler:
     def summary(self):
         torch.cuda.synchronize()
         by = {}
-        for name, fl, e0, e1 in self.records:
+        for name, fl, e0, e1, nbytes in self.records:
             t = e0.elapsed_time(e1) * 1e-3
-            f, tt, n = by.get(name, (0.0, 0.0, 0))
-            by[name] = (f + fl, tt + t, n + 1)
+            f, tt, n, bb = by.get(name, (0.0, 0.0, 0, 0.0))
+            by[name] = (f + fl, tt + t, n + 1, bb + nbytes)
         tot_f = sum(v[0] for v in by.values()); tot_t = sum(v[1] for v in by.values())
         oth = {}
         for name, e0, e1 in self.other:
@@ -344,11 +354,13 @@ def run_b200(args):
     result_host = torch.empty(T, N, 1, dtype=torch.float32, pin_memory=True)
 
     # Double-buffered upload: rollout i+1 is copied from pinned host memory into a second obs buffer while update i
-    # runs.  Host->device transfers share one DMA queue with the expert-batch prefetch of Discriminator.update, so the
-    # rollout copy is enqueued (one async copy on its own stream) when the discriminator epochs are over and overlaps
-    # predict_reward + GAE + PPO.update, whose inputs are all on the device.  This is how the storage is fed in the
-    # reference flow too - insert() copies one time slice per env step while the simulator runs (tools/learn.py:111-133).
-    # Every timed step issues and completes one full rollout upload; the small tensors go on the compute stream.
+    # runs.  Host->device transfers are served in submission order by one DMA queue (55 GB/s, idle or under load:
+    # profiles/r01_h2d_bandwidth.txt) that the expert-batch prefetch of Discriminator.update also uses, so the rollout
+    # goes up in chunks: one chunk is enqueued (on its own stream) each time the discriminator pulls the next expert batch,
+    # sized so that chunk + expert batch fit inside one minibatch of compute, and the rest when the discriminator epochs
+    # are over, overlapping predict_reward + GAE + PPO.update.  This is how the storage is fed in the reference flow too
+    # - insert() copies one time slice per env step while the simulator runs (tools/learn.py:111-133).  Every timed step
+    # issues and completes one full rollout upload; the small tensors go on the compute stream.
     up_stream = torch.cuda.Stream(device=dev)
     try:
         obs_bufs = [ro.obs, torch.empty_like(ro.obs)]
@@ -358,20 +370,51 @@ def run_b200(args):
         double = False
     small = [k for k in names if k != "obs"]
     uploaded = [torch.cuda.Event(), torch.cuda.Event()]
-    state = {"i": 0}
+    state = {"i": 0, "chunk": 0}
+    flat_host = host["obs"].view(-1)
+    NCH = 24
+    per = (flat_host.numel() + NCH - 1) // NCH
+
+    def enqueue_chunks(j, upto):
+        """Copy chunks [state.chunk, upto) of the next rollout into obs_bufs[j]; record the event after the last one."""
+        flat = obs_bufs[j].view(-1)
+        with torch.cuda.stream(up_stream):
+            while state["chunk"] < min(upto, NCH):
+                o = state["chunk"] * per
+                flat[o:o + per].copy_(flat_host[o:o + per], non_blocking=True)
+                state["chunk"] += 1
+            if state["chunk"] == NCH:
+                uploaded[j].record(up_stream)
 
     def enqueue_upload(j):
         up_stream.wait_stream(torch.cuda.current_stream())  # (serial mode: the buffer is the live one)
-        with torch.cuda.stream(up_stream):
-            obs_bufs[j].copy_(host["obs"], non_blocking=True)
-            uploaded[j].record(up_stream)
+        state["chunk"] = 0
+        enqueue_chunks(j, NCH)
+
+    class InterleavedLoader:
+        """The expert loader, with one rollout chunk enqueued ahead of every expert batch after the first."""
+        def __init__(self, inner):
+            self.inner, self.batch_size = inner, inner.batch_size
+        def __len__(self):
+            return len(self.inner)
+        def __iter__(self):
+            for k, batch in enumerate(self.inner):
+                if double and k > 0 and state["chunk"] < NCH - 8:
+                    enqueue_chunks((state["i"] + 1) % 2, state["chunk"] + 1)
+                yield batch
 
     rewards_orig = disc.predict_rewards_rollout
 
     def rewards_hook(rollouts):
         if double:
-            enqueue_upload((state["i"] + 1) % 2)
+            enqueue_chunks((state["i"] + 1) % 2, NCH)
         return rewards_orig(rollouts)
+
+    loader_e2e = InterleavedLoader(loader)
+
+    def step_inner():
+        return update_iteration(pol, agent, disc, ro, loader_e2e, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
+                                gail_epoch=c["gail_epoch"], bcgail=False, diagnostics=False)
 
     def step_e2e():
         i = state["i"]
@@ -381,7 +424,8 @@ def run_b200(args):
         ro.obs = obs_bufs[i % 2]
         for k in small:
             getattr(ro, k).copy_(host[k], non_blocking=True)
-        out = step()                                      # tuples are read back inside (one D2H per update call)
+        state["chunk"] = 0
+        out = step_inner()                                # tuples are read back inside (one D2H per update call)
         result_host.copy_(ro.returns[:-1], non_blocking=True)   # the step's result tensor back to the host
         torch.cuda.current_stream().synchronize()
         state["i"] = i + 1
@@ -420,12 +464,25 @@ def run_b200(args):
     by, tot_f, tot_t = prof.summary()
     step_s = dt / args.steps
     tf32_peak = pk["bf16"] / 2.0
+    # DRAM traffic of the contraction that takes the most time in the step (conv1 fprop, one launch at B=4096), from the
+    # committed `ncu --set full` capture (profiles/r01_ncu_traffic.json; algorithmic bytes of that launch: 7.15e9)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp)).get("r01_conv1_fprop_full")
+        if tj:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_src = "profiles/r01_ncu_traffic.json: gc_conv_fprop[16->32] B=4096, one launch (algorithmic 7.15e9 B, %.3f ms)" % (tj["seconds"] * 1e3)
     roof = {"bound": "tensor", "kernel": "umma_gemm_kernel (tcgen05.mma.kind::tf32, all conv/linear contractions)",
             "achieved": tot_f / tot_t / 1e12 if tot_t else None, "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": (tot_f / tot_t / 1e12) / tf32_peak if tot_t else None, "traffic": None,
+            "frac": (tot_f / tot_t / 1e12) / tf32_peak if tot_t else None, "traffic": traffic, "traffic_note": traffic_src,
             "peak_note": f"TF32 dense = 1/2 of the {pk['src']} sustained bf16 peak ({pk['bf16']} TF/s); MEASURED_PEAKS.json has no TF32 entry",
             "share_of_step": tot_t / step_s if step_s else None, "launches": len(prof.records),
-            "per_op": {k: {"tflops": v[0] / v[1] / 1e12, "seconds": v[1], "launches": v[2]} for k, v in by.items()}}
+            # per contraction: tensor-pipe rate, and for the convolutions the algorithmic HBM rate (the small-channel layers
+            # conv1 / conv2 are HBM-bound: ~17 and ~80 FLOP per byte moved)
+            "per_op": {k: dict({"tflops": v[0] / v[1] / 1e12, "seconds": v[1], "launches": v[2]},
+                               **({"hbm_gbs": v[3] / v[1] / 1e9, "hbm_frac": v[3] / v[1] / 1e9 / pk["hbm"]} if v[3] else {}))
+                       for k, v in by.items()}}
 
     if rank == 0:
         hbm = hbm_microbench(A, dev, pk) if world == 1 else None
