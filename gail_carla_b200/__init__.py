@@ -6,6 +6,7 @@ Drop-in classes (same names and call signatures as the reference modules they re
     RunningMeanStd  <- common/running_mean_std.py
 All arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI in include/gail_carla_b200.h; there is no
 CPU fallback - importing works anywhere, calling needs the built library and a CUDA device.
+The training iteration around them (tools/learn.py) is `gail_carla_b200.learn.gail_learning`.
 """
 from .storage import RolloutStorage
 from .model import Policy

@@ -96,3 +96,78 @@ class SyntheticExpertLoader:
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
         return iter(self._batches)
+
+
+class _Space:
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+class SyntheticVecEnv:
+    """Simulator-free stand-in for the reference's vectorised CARLA env (tools/envs.py; carla_env.py:93-100,134-147):
+    same protocol - ``reset() -> (obs[N,3,192,192], metrics[N,4])``, ``step(action[N,2]) -> (obs, metrics,
+    rewards[N,1], done[N], infos[N])``, ``observation_space / metrics_space / action_space`` with ``.shape``;
+    ``infos[i]`` carries ``{'episode': {'r', 'l'}, 'route_id'}`` when env i finishes an episode
+    (tools/learn.py:121-126).  Observations are drawn on `device` (the rollout never visits the host); episodes end
+    with probability ``1/mean_episode_len`` per step; the env reward is minus the squared steering command, only so
+    that episode returns depend on the actions."""
+
+    def __init__(self, num_envs: int, seed: int = 3, device="cpu", mean_episode_len: int = 400, routes=(0,)):
+        self.num_envs, self.device = num_envs, torch.device(device)
+        self.observation_space, self.metrics_space, self.action_space = _Space(OBS_SHAPE), _Space(METRICS_SHAPE), _Space(ACTION_SHAPE)
+        self._g = _gen(seed, self.device.type if self.device.type == "cpu" else self.device)
+        self._cpu = _gen(seed + 1)
+        self._p_end = 1.0 / float(mean_episode_len)
+        self._routes = tuple(routes)
+        self._ret = [0.0] * num_envs
+        self._len = [0] * num_envs
+        self._route = [self._routes[i % len(self._routes)] for i in range(num_envs)]
+        self.epoch = 0
+
+    def set_epoch(self, epoch: int) -> None:     # tools/envs.py EnvEpoch.set_epoch
+        self.epoch = epoch
+
+    def _draw(self):
+        return synth_obs(self.num_envs, self._g, self.device), synth_metrics(self.num_envs, self._g, self.device)
+
+    def reset(self):
+        self._ret = [0.0] * self.num_envs
+        self._len = [0] * self.num_envs
+        return self._draw()
+
+    def step(self, action):
+        a = torch.as_tensor(action).detach().float().reshape(self.num_envs, -1).cpu()
+        obs, metrics = self._draw()
+        rewards = -(a[:, :1] ** 2)
+        done = (torch.rand(self.num_envs, generator=self._cpu) < self._p_end).tolist()
+        infos = []
+        for i in range(self.num_envs):
+            self._ret[i] += float(rewards[i, 0])
+            self._len[i] += 1
+            info = {}
+            if done[i]:
+                info = {"episode": {"r": self._ret[i], "l": self._len[i]}, "route_id": self._route[i]}
+                self._ret[i], self._len[i] = 0.0, 0
+            infos.append(info)
+        return obs, metrics, rewards, done, infos
+
+
+class SyntheticEvalEnv:
+    """Single evaluation env with a fixed episode length (tools/learn.py:225-252 protocol: unbatched obs / metrics,
+    ``step(action[2]) -> (obs, metrics, reward, done, info)``, ``ep_length``)."""
+
+    def __init__(self, ep_length: int = 16, seed: int = 5, device="cpu"):
+        self.ep_length, self.device = ep_length, torch.device(device)
+        self._g = _gen(seed, self.device.type if self.device.type == "cpu" else self.device)
+        self._t, self._ret = 0, 0.0
+
+    def reset(self):
+        self._t, self._ret = 0, 0.0
+        return synth_obs(1, self._g, self.device)[0], synth_metrics(1, self._g, self.device)[0]
+
+    def step(self, action):
+        self._t += 1
+        self._ret += -float(action[0]) ** 2
+        done = self._t >= self.ep_length - 1
+        info = {"episode": {"r": self._ret, "l": self._t}} if done else {}
+        return synth_obs(1, self._g, self.device)[0], synth_metrics(1, self._g, self.device)[0], 0.0, done, info

@@ -1,0 +1,61 @@
+"""GPU run of the training iteration (gail_carla_b200/learn.py) through the C-ABI kernels: rollout collection with the
+device-resident policy, discriminator epochs, batched rewards, GAE, PPO, evaluation episode, checkpoint - and the same
+two iterations on the CPU statements of the ABI (oracle/abi_emu.py) from identical seeds; scalars must agree within the
+TF32 tolerance of the full-update parity tests (5e-2 relative after the discriminator epochs)."""
+import math
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HP = dict(lr=1e-4, eps=1e-8, betas=(0.9, 0.99), clip_param=0.1, value_loss_coef=0.5, max_grad_norm=0.5,
+          gail_lr=2.5e-4, gail_eps=1e-8, gail_betas=(0.9, 0.99), gail_max_grad_norm=0.5, gamma=0.99, gae_lambda=0.95,
+          logstd=[-1.4, -3.2])
+
+
+def _run(device, tmp_path, tag):
+    import gail_carla_b200 as G
+    from gail_carla_b200 import learn as L, synthetic
+    torch.manual_seed(1); np.random.seed(1)
+    nenv, nsteps = 4, 32
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+    pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False)
+    agent = G.PPO(pol, HP["clip_param"], 1, 16, HP["value_loss_coef"], device, lr=HP["lr"], eps=HP["eps"], betas=HP["betas"],
+                  max_grad_norm=HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+    disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, device, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
+                           HP["gail_max_grad_norm"])
+    envs = synthetic.SyntheticVecEnv(nenv, seed=3, device="cpu", mean_episode_len=4, routes=(0,))
+    env_eval = synthetic.SyntheticEvalEnv(ep_length=6, seed=5, device="cpu")
+    train = synthetic.SyntheticExpertLoader(2, 16, seed=21)
+    val = synthetic.SyntheticExpertLoader(1, 16, seed=22)
+    rp = dict(num_steps=nsteps, num_env_steps=2 * nsteps, envs_params=[{}] * nenv, routes=[0], lr=HP["lr"],
+              use_linear_lr_decay=True, gail_epoch=1, gail_pre_epoch=1, gail_thre=0, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
+              bcgail=False, eval_interval=1, log_interval=1, resume_training=False)
+    torch.manual_seed(7)
+    log = L.gail_learning(rp, envs, env_eval, pol, agent, disc, train, val, device, model_path=str(tmp_path / f"{tag}.pt"))
+    return log.history
+
+
+def test_learn_loop_gpu_matches_cpu_statement(tmp_path, monkeypatch):
+    hist_gpu = _run("cuda", tmp_path, "gpu")
+    from gail_carla_b200 import _abi
+    from oracle import abi_emu
+    for name in dir(abi_emu):
+        fn = getattr(abi_emu, name)
+        if callable(fn) and not name.startswith("_") and hasattr(_abi, name) and name not in ("call", "load_library"):
+            monkeypatch.setattr(_abi, name, fn)
+    monkeypatch.setattr(_abi, "EMULATED", True, raising=False)
+    hist_cpu = _run("cpu", tmp_path, "cpu")
+    assert len(hist_gpu) == len(hist_cpu) and len(hist_gpu) >= 4
+    for a, b in zip(hist_gpu, hist_cpu):
+        assert set(a) == set(b)
+        for k in a:
+            if k in ("step", "Eval steps", "Train steps", "steer_std", "throttle_std", "gail_gamma"):
+                assert a[k] == b[k] or (math.isnan(a[k]) and math.isnan(b[k])), k
+            elif math.isnan(b[k]):
+                assert math.isnan(a[k]), k
+            else:
+                assert abs(a[k] - b[k]) <= 5e-2 * abs(b[k]) + 2e-3, (k, a[k], b[k])
