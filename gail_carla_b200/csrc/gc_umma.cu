@@ -139,7 +139,8 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   if (p.b_resident) {
     p.b_bytes = 0;
     p.b_slab_bytes = p.bn * 128;
-    GC_REQUIRE(!pl.b_mn && pl.grid.y == 1 && p.k_iters * p.taps <= 64, "%s: resident-B mode needs K-major B, one n-tile, <= 64 (k,tap) pairs", what);
+    GC_REQUIRE(!pl.b_mn && pl.grid.y == 1 && p.k_iters <= 16 && p.taps <= 4 && p.bk == 32,
+               "%s: resident-B mode needs K-major B, one n-tile, <= 16 k-iterations of <= 4 taps", what);
   } else {
     p.b_slabs = 0; p.b_slab_bytes = 0;
     p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;

@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   uint64_t* bars = (uint64_t*)(staging + (size_t)p.nbuf * 16384);
   // bars: full[stages], empty[stages], tmem_full[2], tmem_empty[2], aux[4], bres
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * p.stages + 9);
-  float* s_bias = (float*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);  // nt*bn floats (<= 512) for bias epilogues
+  // resident-weights mode: low descriptor word of the B slab used by (k-iteration, tap), 4 entries per k-iteration,
+  // filled once by the MMA thread (the per-tap constant-bank lookups were ~100 clocks of its ~105 per MMA)
+  uint32_t* s_btab = (uint32_t*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);
+  float* s_bias = (float*)(s_btab + 64);  // nt*bn floats (<= 512) for bias epilogues
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
@@ -393,10 +396,20 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       const uint32_t bres_u32 = smem_u32(bres), b_slab = (uint32_t)p.b_slab_bytes, a_off0 = (uint32_t)p.exp_a_off;
       const uint32_t smem0 = smem_u32(smem), a_bytes = (uint32_t)p.a_bytes, b_off = (uint32_t)p.exp_b_off;
       const int k_iters = p.k_iters, stages = p.stages, ngroups = p.ngroups;
-      int tap_off[4];
+      uint32_t gb[8], ga[8];   // slab mode: per-group B descriptor constant and TMEM column offset (<= 8 groups, host-checked)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) tap_off[t] = p.tap_off[t];
+      for (int g = 0; g < 8; ++g) {
+        gb[g] = SLAB ? b_lo_base + ((uint32_t)p.grp_b_off[g] >> 4) : 0u;
+        ga[g] = SLAB ? (uint32_t)p.grp_acc[g] : 0u;
+      }
+      uint32_t ta[4];   // per-tap A descriptor constants (taps are shifted views of one staged patch)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) ta[t] = a_lo_base + ((a_off0 + (uint32_t)p.tap_off[t]) >> 4);
+      const uint32_t s_btab_u32 = smem_u32(s_btab);
       if (p.b_resident) {
+        for (int i = 0; i < k_iters; ++i)
+          for (int t = 0; t < 4; ++t)
+            s_btab[i * 4 + t] = t < n_taps ? b_lo_base + ((bres_u32 + (uint32_t)p.b_tab[i * n_taps + t] * b_slab) >> 4) : 0u;
         mbar_wait(bres_bar, 0);
         tc_fence_after();
       }
@@ -407,8 +420,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         mbar_wait_t(tempty0 + 8 * acc, aph ^ 1, timed, w_tempty);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(acc * acc_cols);
-        int kt = 0;
-        for (int k = 0; k < k_iters; ++k, kt += n_taps) {
+        for (int k = 0; k < k_iters; ++k) {
           mbar_wait_t(full0 + 8 * s, ph, timed, w_full);
           tc_fence_after();
           const uint32_t sa = smem0 + (uint32_t)s * (uint32_t)stage_bytes, sb = sa + a_bytes;
@@ -417,25 +429,43 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           // only N/2 cycles, so the single issuing thread must not spend more than that per instruction).
           if constexpr (SLAB) {
             // slab mode: every group multiplies the same A slab with its own shifted view of the B patches
-            const uint32_t alo = a_lo_base + (sa >> 4);
-            for (int g = 0; g < ngroups; ++g) {
-              const uint32_t blo = b_lo_base + ((sb + (uint32_t)p.grp_b_off[g]) >> 4);
-              const uint32_t tg = tacc + (uint32_t)p.grp_acc[g];
-              for (int ks = 0; ks < ksteps; ++ks)
-                umma_tf32(tg, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
+            const uint32_t alo = a_lo_base + (sa >> 4), sb4 = sb >> 4;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g < ngroups) {
+                const uint32_t blo = sb4 + gb[g], tg = tacc + ga[g];
+                for (int ks = 0; ks < ksteps; ++ks)
+                  umma_tf32(tg, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
+              }
             }
           } else {
-            for (int t = 0; t < n_taps; ++t) {
-              const uint32_t alo = a_lo_base + ((sa + a_off0 + (uint32_t)tap_off[t]) >> 4);
-              const uint32_t blo = b_lo_base + ((b_res ? bres_u32 + (uint32_t)p.b_tab[kt + t] * b_slab : sb + b_off) >> 4);
+            if (b_res && ksteps == 4) {
+              // patch modes: every descriptor is (stage base >> 4) + a per-tap constant (A) or a table entry (B)
+              const uint32_t sa4 = sa >> 4;
+              uint32_t bl[4];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bl[0]), "=r"(bl[1]), "=r"(bl[2]), "=r"(bl[3])
+                           : "r"(s_btab_u32 + (uint32_t)k * 16u) : "memory");
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                if (t < n_taps) {
+                  const uint32_t alo = sa4 + ta[t], blo = bl[t];
+                  umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
+                  umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
+                  umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
+                  umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
+                }
+              }
+            } else {
+              const uint32_t alo = a_lo_base + ((sa + a_off0) >> 4);
+              const uint32_t blo = b_lo_base + ((sb + b_off) >> 4);
               if (ksteps == 4) {
-                umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
+                umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, k ? 1u : 0u);
                 umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
                 umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
                 umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
               } else {
                 for (int ks = 0; ks < ksteps; ++ks)
-                  umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | t | ks) ? 1u : 0u);
+                  umma_tf32(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
               }
             }
           }

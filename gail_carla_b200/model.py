@@ -197,7 +197,9 @@ class Policy(nn.Module):
         with torch.no_grad():
             eng, head, B = self._run(obs, metrics)
             dev = head.device
-            noise = None if deterministic else torch.randn(B, 2, device=dev)
+            # Normal.sample() of the reference = mean + std * N(0,1) drawn from the default generator; the draw stays on
+            # the host generator (B x 2 floats) so a GPU run consumes the same random stream as the CPU oracle
+            noise = None if deterministic else torch.randn(B, 2).to(dev, non_blocking=True)
             value = torch.empty(B, 1, device=dev); action = torch.empty(B, 2, device=dev); logp = torch.empty(B, 1, device=dev)
             A.policy_act(head, noise, value, action, logp, B, self.base.logstd.tolist(), self.base.activation)
             return value, action, logp
