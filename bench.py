@@ -284,6 +284,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
         dist.init_process_group("nccl", device_id=dev)
     A.load_library()
     prof = Profiler(A)

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "gc_policy_act": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _P],
     "gc_welford_merge": [_P, _P, _L, _P, _P],
     "gc_gather_obs_s2d": [_P, _P, _P, _I, _P],
+    "gc_gather_obs_u8_s2d": [_P, _P, _P, _I, _P],
     "gc_gather_rows": [_P, _P, _P, _I, _I, _L, _P],
     "gc_mixup": [_P, _P, _P, _P, _I, _L, _P],
     "gc_metrics_features": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
@@ -151,8 +152,12 @@ def welford_merge(state, x, scratch2):
 
 # ------------------------------------------------------------------ data movement / small stages
 def gather_obs_s2d(src, idx, out, B):
+    """src: fp32 rows [*,3,192,192], or the uint8 table of a device-resident expert data set (decoded PNG bytes)."""
     _contig(src, idx, out)
-    call("gc_gather_obs_s2d", _ptr(src), _ptr(idx, torch.int64), _ptr(out), B, _stream())
+    if src.dtype == torch.uint8:
+        call("gc_gather_obs_u8_s2d", _ptr(src, torch.uint8), _ptr(idx, torch.int64), _ptr(out), B, _stream())
+    else:
+        call("gc_gather_obs_s2d", _ptr(src), _ptr(idx, torch.int64), _ptr(out), B, _stream())
 
 
 def gather_rows(src, idx, out, B, width, ldo):

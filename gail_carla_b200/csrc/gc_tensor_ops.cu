@@ -22,16 +22,25 @@ inline int grid_for(long n, int threads, int per_sm) {
 // One CTA per (sample, group of 4 s2d rows): stage 4 x 3 channels x 2 image rows x 192 floats in smem with float4
 // loads (3 independent 16-byte loads in flight per thread), then write the 4 x 96 x 16 output floats contiguously.
 constexpr int kGatherRows = 4;
-__global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const float* __restrict__ src, const long long* __restrict__ idx,
+// source element -> 4 consecutive pixels of one image row as floats in [0,1]
+__device__ __forceinline__ float4 load_px4(const float* row, int xv) { return __ldg(reinterpret_cast<const float4*>(row) + xv); }
+__device__ __forceinline__ float4 load_px4(const unsigned char* row, int xv) {
+  // expert images are stored as the PNGs' uint8 (algo/wdgail.py:222-227: ToTensor = uint8 / 255 in fp32)
+  const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(row) + xv);
+  return make_float4((float)u.x / 255.f, (float)u.y / 255.f, (float)u.z / 255.f, (float)u.w / 255.f);
+}
+
+template <typename SrcT>
+__global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const SrcT* __restrict__ src, const long long* __restrict__ idx,
                                                              float* __restrict__ out) {
   __shared__ __align__(16) float tile[kGatherRows][kObsC][2][kObsW + 4];
   const int b = blockIdx.y, Y0 = blockIdx.x * kGatherRows;
   const long row = idx ? idx[b] : b;
-  const float4* s4 = reinterpret_cast<const float4*>(src + row * (long)(kObsC * kObsH * kObsW));
-  constexpr int kRowV = kObsW / 4;  // float4 per image row
+  const SrcT* img = src + row * (long)(kObsC * kObsH * kObsW);
+  constexpr int kRowV = kObsW / 4;  // 4-pixel groups per image row
   for (int i = threadIdx.x; i < kGatherRows * kObsC * 2 * kRowV; i += blockDim.x) {
     const int xv = i % kRowV, dy = (i / kRowV) % 2, c = (i / (2 * kRowV)) % kObsC, yy = i / (2 * kRowV * kObsC);
-    float4 v = __ldg(s4 + ((long)c * kObsH + 2 * (Y0 + yy) + dy) * kRowV + xv);
+    const float4 v = load_px4(img + ((long)c * kObsH + 2 * (Y0 + yy) + dy) * kObsW, xv);
     const float m = c_mean[c], sd = c_std[c];
     *reinterpret_cast<float4*>(&tile[yy][c][dy][4 * xv]) =
         make_float4((v.x - m) / sd, (v.y - m) / sd, (v.z - m) / sd, (v.w - m) / sd);
@@ -407,8 +416,16 @@ int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B,
   GC_REQUIRE(src && out && B > 0, "gc_gather_obs_s2d: bad arguments");
   GC_REQUIRE(B <= 65535, "gc_gather_obs_s2d: B=%d exceeds grid.y", B);
   GC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_s2d: pointers must be 16-byte aligned");
-  gather_obs_s2d_kernel<<<dim3(kS2dH / kGatherRows, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
+  gather_obs_s2d_kernel<float><<<dim3(kS2dH / kGatherRows, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
   return gc::launch_status("gather_obs_s2d_kernel");
+}
+
+int gc_gather_obs_u8_s2d(const unsigned char* src, const long long* idx, float* out, int B, void* stream) {
+  GC_REQUIRE(src && out && B > 0, "gc_gather_obs_u8_s2d: bad arguments");
+  GC_REQUIRE(B <= 65535, "gc_gather_obs_u8_s2d: B=%d exceeds grid.y", B);
+  GC_REQUIRE(((uintptr_t)src & 3) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_u8_s2d: src must be 4-byte, out 16-byte aligned");
+  gather_obs_s2d_kernel<unsigned char><<<dim3(kS2dH / kGatherRows, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
+  return gc::launch_status("gather_obs_s2d_kernel<u8>");
 }
 
 int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream) {

@@ -14,6 +14,7 @@ import torch
 import torch.distributed as dist
 
 from . import _abi as A
+from .expert import expert_rows
 from .optim import FusedClipAdam
 
 
@@ -65,16 +66,18 @@ class PPO():
                 Be = 0
                 e_act = None
                 if use_bc:   # algo/ppo.py:88-102: first batch of a fresh iterator over the expert loader
-                    for exp_state, exp_metrics, exp_action in expert_dataset:
-                        Be = exp_state.shape[0]
-                        e_obs = exp_state.to(dev, torch.float32, non_blocking=True).contiguous()
-                        e_met = exp_metrics.to(dev, torch.float32, non_blocking=True).contiguous()
-                        e_act = exp_action.to(dev, torch.float32, non_blocking=True).contiguous()
+                    for e_batch in expert_dataset:
+                        e_obs, e_met, e_act_rows, e_idx, Be = expert_rows(e_batch, dev)
                         break
                 ws = eng.workspace(B + Be)
                 eng.load_inputs(obs_rows, met_rows, idx, B)
                 if Be:
-                    eng.load_inputs(e_obs, e_met, None, Be, row0=B)
+                    eng.load_inputs(e_obs, e_met, e_idx, Be, row0=B)
+                    if e_idx is None:
+                        e_act = e_act_rows
+                    else:   # device-resident expert table: gather the batch's action rows
+                        e_act = ws.buf("e_act", ws.rows, 2)
+                        A.gather_rows(e_act_rows, e_idx, e_act, Be, 2, 2)
                 a_b = ws.buf("act", ws.rows, 2); vo_b = ws.buf("vold", ws.rows); r_b = ws.buf("ret", ws.rows)
                 lp_b = ws.buf("olp", ws.rows)
                 A.gather_rows(act_rows, idx, a_b, B, 2, 2)

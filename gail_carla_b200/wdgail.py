@@ -23,6 +23,7 @@ from . import _abi as A
 from . import engine as E
 from ._abi import LDF, S2D_PER_SAMPLE, EPI_BIAS_LRELU, EPI_MASK, EPI_STORE
 from .model import _Holder, _conv_seq, N_METRIC_FEAT
+from .expert import DeviceBatch, expert_rows
 from .optim import FusedClipAdam
 from .running_mean_std import RunningMeanStd
 
@@ -226,7 +227,7 @@ class Discriminator(nn.Module):
         dev = self._dev()
         if dev.type != "cuda":
             for batch, idx in pairs:
-                yield self._to_dev(*batch), idx, (lambda: None)
+                yield (batch if isinstance(batch, DeviceBatch) else self._to_dev(*batch)), idx, (lambda: None)
             return
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -238,6 +239,9 @@ class Discriminator(nn.Module):
 
         def stage(pair, k):
             batch, idx = pair
+            if isinstance(batch, DeviceBatch):               # device-resident expert data: nothing to copy
+                ready[k].record(main)
+                return batch, idx
             bufs = self._stage_bufs[k]
             if bufs is None or any(b.shape != t.shape for b, t in zip(bufs, batch)):
                 bufs = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in batch]
@@ -306,11 +310,12 @@ class Discriminator(nn.Module):
             import itertools
             pairs = itertools.chain([first], pairs) if first is not None else iter(())
         with torch.no_grad():
-            for i_batch, ((e_obs, e_met, e_act), idx, release) in enumerate(self._prefetched(pairs)):
-                if e_obs.shape[0] != B:
+            for i_batch, (e_batch, idx, release) in enumerate(self._prefetched(pairs)):
+                e_obs, e_met, e_act, e_idx, e_rows = expert_rows(e_batch, dev)
+                if e_rows != B:
                     raise ValueError("expert batches must all have expert_loader.batch_size rows (drop_last=True)")
                 eng.workspace(3 * B)
-                eng.load_inputs(e_obs, e_met, e_act, None, B, 0)
+                eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
                 release()
                 eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
                 if alphas is not None and i_batch < alphas.shape[0]:
@@ -339,7 +344,8 @@ class Discriminator(nn.Module):
         with torch.no_grad():
             for expert_batch, idx in zip(expert_loader, rollouts.minibatch_indices(B, batch_size)):
                 eng.workspace(3 * B)
-                eng.load_inputs(*self._to_dev(*expert_batch), None, B, 0)
+                e_obs, e_met, e_act, e_idx, _ = expert_rows(expert_batch, dev)
+                eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
                 eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
                 eng.tail_features(B, 0); eng.tail_features(B, B)
                 d = eng.forward(2 * B)

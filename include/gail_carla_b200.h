@@ -68,8 +68,12 @@ int gc_welford_merge(double* state, const float* x, long n, double* scratch2, vo
 
 /* Minibatch image gather - tools/storage.py:65-66 + tools/model.py:157-161 (normalise).
  * src [rows,3,192,192] fp32 (CHW); idx (nullable) int64[B] row indices (null => rows 0..B-1).
- * out [B,96,96,16] space-to-depth NHWC: out[b,Y,X,dy*8+dx*4+c] = (src[idx[b],c,2Y+dy,2X+dx]-mean[c])/std[c], channel 3 = 0. */
+ * out [B,96,96,16] space-to-depth NHWC: out[b,Y,X,dy*8+dx*4+c] = (src[idx[b],c,2Y+dy,2X+dx]-mean[c])/std[c], channel 3 = 1
+ * (the ones column that turns conv1's bias gradient into a wgrad column; its conv1 weight is 0). */
 int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B, void* stream);
+/* Same from a uint8 table [rows,3,192,192] (the expert data set as its PNGs store it - algo/wdgail.py:222-241 decodes each
+ * image to uint8 and ToTensor() divides by 255): out = ((float)src/255 - mean)/std, bit-identical to decoding first. */
+int gc_gather_obs_u8_s2d(const unsigned char* src, const long long* idx, float* out, int B, void* stream);
 
 /* out[b, 0:width] = src[idx[b], 0:width] (idx nullable), out row pitch ldo - tools/storage.py:66-76 scalar columns. */
 int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream);

@@ -137,6 +137,8 @@ def welford_merge(state, x, scratch2):
 def gather_obs_s2d(src, idx, out, B):
     rows = src.reshape(-1, 3, 192, 192)
     x = rows[idx[:B]] if idx is not None else rows[:B]
+    if x.dtype == torch.uint8:          # device-resident expert table: ToTensor() = uint8 / 255 (algo/wdgail.py:222-227)
+        x = x.float() / 255.0
     mean = torch.tensor(NORM_MEAN).view(1, 3, 1, 1); std = torch.tensor(NORM_STD).view(1, 3, 1, 1)
     x = (x - mean) / std
     x4 = torch.cat([x, torch.ones(B, 1, 192, 192)], 1)                       # [B,4,192,192], pad channel = 1

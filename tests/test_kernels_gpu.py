@@ -141,6 +141,17 @@ def test_gather_mixup_metrics():
         o_ref = torch.zeros(B, 96, 96, 16); E.gather_obs_s2d(src, ix, o_ref, B)
         o = torch.zeros(B, 96, 96, 16, device=DEV); A.gather_obs_s2d(src.to(DEV), None if ix is None else ix.to(DEV), o, B)
         close(o, o_ref, 1e-6, 1e-6, "gather_obs")
+    # uint8 table of a device-resident expert data set: decoding first (uint8/255 -> fp32 rows) and gathering those rows
+    # with the fp32 kernel must give the same bits as the fused uint8 kernel; both within rounding of the CPU statement
+    src8 = torch.randint(0, 256, (rows, 3, 192, 192), generator=g, dtype=torch.uint8)
+    for ix in (idx, None):
+        ixd = None if ix is None else ix.to(DEV)
+        o8 = torch.zeros(B, 96, 96, 16, device=DEV); A.gather_obs_s2d(src8.to(DEV), ixd, o8, B)
+        of = torch.zeros(B, 96, 96, 16, device=DEV); A.gather_obs_s2d((src8.float() / 255).to(DEV), ixd, of, B)
+        close(o8, of, 0, 0, "gather_obs uint8 vs decoded fp32")
+        o_ref = torch.zeros(B, 96, 96, 16); E.gather_obs_s2d(src8, ix, o_ref, B)
+        close(o8, o_ref, 1e-6, 1e-6, "gather_obs uint8")
+        assert (o8.view(B, 96, 96, 4, 4)[..., 3] == 1).all(), "pad channel must hold 1.0"
     s2 = torch.randn(rows, 4, generator=g)
     o_ref = torch.zeros(B, 8); E.gather_rows(s2, idx, o_ref, B, 4, 8)
     o = torch.zeros(B, 8, device=DEV); A.gather_rows(s2.to(DEV), idx.to(DEV), o, B, 4, 8)
