@@ -411,10 +411,10 @@ def run_b200(args):
             enqueue_chunks((state["i"] + 1) % 2, NCH)
         return rewards_orig(rollouts)
 
-    loader_e2e = InterleavedLoader(loader)
+    e2e_loader = {"l": InterleavedLoader(loader)}
 
     def step_inner():
-        return update_iteration(pol, agent, disc, ro, loader_e2e, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
+        return update_iteration(pol, agent, disc, ro, e2e_loader["l"], gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
                                 gail_epoch=c["gail_epoch"], bcgail=False, diagnostics=False)
 
     def step_e2e():
@@ -452,10 +452,31 @@ def run_b200(args):
     step_e2e()
     dt_e2e = timed_e2e(args.steps)
     torch.cuda.synchronize()
+    e2e = env_steps * args.steps / dt_e2e
+    h2d_rollout = sum(v.numel() * 4 for v in host.values())
+
+    # ---- same, with the (static) expert data set resident in HBM as the uint8 bytes its PNGs hold (SURVEY 8f row 3,
+    # gail_carla_b200/expert.py): only the rollout crosses PCIe.  Reported next to `e2e`, not instead of it.
+    e2e_res = None
+    try:
+        from gail_carla_b200.expert import DeviceExpertLoader, ExpertDataset
+        ds = ExpertDataset.from_tensors(torch.cat([(b[0] * 255.0).round().to(torch.uint8) for b in loader]),
+                                        torch.cat([b[1] for b in loader]), torch.cat([b[2] for b in loader]))
+        e2e_loader["l"] = InterleavedLoader(DeviceExpertLoader(ds, Bg, shuffle=False, drop_last=True, device=dev))
+        del ds
+        step_e2e()
+        dt_res = timed_e2e(args.steps)
+        torch.cuda.synchronize()
+        e2e_res = {"value": env_steps * args.steps / dt_res, "unit": "env-steps/s", "ms_per_step": dt_res / args.steps * 1e3,
+                   "h2d_bytes_per_step": h2d_rollout * world, "d2h_bytes_per_step": (result_host.numel() * 4 + 8 * 15) * world,
+                   "note": "expert data set resident in HBM as uint8 (uploaded once, outside the timed region); the rollout "
+                           "is uploaded from pinned host memory every step as in `e2e`"}
+    except RuntimeError as ex:                              # e.g. no room for the table
+        e2e_res = {"unavailable": str(ex)[:200]}
+    e2e_loader["l"] = None
     disc.predict_rewards_rollout = rewards_orig
     ro.obs = obs_bufs[0]
     del obs_bufs[1:]
-    e2e = env_steps * args.steps / dt_e2e
     d2h = result_host.numel() * 4 + 8 * 15
 
     # ---- instrumented step: per-contraction CUDA events -> tensor-pipe roofline of the dominant kernel
@@ -499,6 +520,7 @@ def run_b200(args):
                         "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned,
                         "upload": ("double-buffered" if double else "serial") + ": rollout i+1 is copied from pinned host memory behind "
                                   "predict_reward + PPO.update of step i; one full rollout upload + all expert batches per timed step"},
+                "e2e_expert_resident": e2e_res,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu,
                 "other_kernels_seconds": prof.other_summary}
         print(json.dumps(line), flush=True)

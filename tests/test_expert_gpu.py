@@ -1,6 +1,9 @@
 """GPU: a discriminator update, compute_loss and a BC-mixed PPO update fed by the device-resident DeviceExpertLoader
-(uint8 table in HBM, fused uint8 gather) must equal - bit for bit - the same steps fed by the reference-style host fp32
-batches of the same samples (the kernels see identical normalised images either way)."""
+(uint8 table in HBM, fused uint8 gather) against the same steps fed by the reference-style host fp32 batches of the same
+samples.  The kernels see bit-identical normalised images either way (test_kernels_gpu.py::test_gather_mixup_metrics);
+the update itself is only reproducible up to the order of its fp32 / fp64 atomic reductions (bias column sums, gradient
+norms), so scalars are compared at rtol 1e-5 and parameters with the Adam-step bound of the parity tests
+(max |diff| <= 2.5*lr per step, mean |diff| <= 0.05*lr)."""
 import os
 from types import SimpleNamespace as NS
 
@@ -54,7 +57,8 @@ def test_resident_expert_data_equals_host_batches_on_gpu():
                         {k: v.detach().cpu().clone() for k, v in pol.state_dict().items()}))
     a, b = results
     for i in range(3):
-        np.testing.assert_array_equal(np.asarray(a[i]), np.asarray(b[i]))
-    for sd_a, sd_b in ((a[3], b[3]), (a[4], b[4])):
+        np.testing.assert_allclose(np.asarray(a[i]), np.asarray(b[i]), rtol=1e-5, atol=1e-7)
+    for sd_a, sd_b, lr, steps in ((a[3], b[3], HP["gail_lr"], 2), (a[4], b[4], HP["lr"], 2)):
         for k in sd_a:
-            assert torch.equal(sd_a[k], sd_b[k]), k
+            d = (sd_a[k].double() - sd_b[k].double()).abs()
+            assert d.max().item() <= 2.5 * lr * steps and d.mean().item() <= 0.05 * lr, (k, d.max().item(), d.mean().item())
