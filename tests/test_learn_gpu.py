@@ -61,3 +61,35 @@ def test_learn_loop_gpu_matches_cpu_statement(tmp_path, monkeypatch):
                 assert math.isnan(a[k]), k
             else:
                 assert abs(a[k] - b[k]) <= 5e-2 * abs(b[k]) + 5e-2, (k, a[k], b[k])
+
+
+def test_learn_bc_gpu_matches_cpu_statement(tmp_path, monkeypatch):
+    """learn_bc.py:15-72 on the device-resident expert table: GPU (TF32 trunk) vs the CPU statement of the ABI from the
+    same seeds - epoch losses within 2e-3 relative (the tolerance of the TF32 contractions)."""
+    import os
+    import gail_carla_b200 as G
+    from conftest import GOLDEN
+    from gail_carla_b200 import synthetic
+    from gail_carla_b200.expert import DeviceExpertLoader, ExpertDataset
+    from gail_carla_b200.learn_bc import learn_bc
+    ds = ExpertDataset(os.path.join(GOLDEN, "expert_ds"), routes=[0, 3], n_eps=1)
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+
+    def run(device):
+        torch.manual_seed(1)
+        pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False)
+        train = DeviceExpertLoader(ds, 4, shuffle=True, drop_last=True, device=device)
+        val = DeviceExpertLoader(ds, 3, shuffle=False, drop_last=True, device=device)
+        torch.manual_seed(9)
+        return learn_bc(pol, device, train, val, episodes=2, lr=3e-4, save_path=str(tmp_path / f"bc_{device}.pt"))
+
+    gpu = run("cuda")
+    from gail_carla_b200 import _abi
+    from oracle import abi_emu
+    for name in dir(abi_emu):
+        fn = getattr(abi_emu, name)
+        if callable(fn) and not name.startswith("_") and hasattr(_abi, name) and name not in ("call", "load_library"):
+            monkeypatch.setattr(_abi, name, fn)
+    monkeypatch.setattr(_abi, "EMULATED", True, raising=False)
+    cpu = run("cpu")
+    np.testing.assert_allclose(np.asarray(gpu), np.asarray(cpu), rtol=2e-3, atol=1e-4)
