@@ -76,10 +76,10 @@ def test_gae_constant_reward_closed_form():
     close(ret[:T, 7, 0], expect, 1e-5, 1e-6, "closed form")
 
 
+@pytest.mark.parametrize("B", [1000, 1003, 3])     # 4 samples per thread + ragged tail
 @pytest.mark.parametrize("mode,use_adv", [(0, True), (0, False), (1, False), (2, False)])
-def test_ppo_loss_vs_autograd(mode, use_adv):
+def test_ppo_loss_vs_autograd(mode, use_adv, B):
     A, E = _abi(), _emu()
-    B = 1000
     g = torch.Generator().manual_seed(5 + mode)
     head = torch.randn(B, 4, generator=g); act = torch.randn(B, 2, generator=g) * 0.3
     act[:, 1] = act[:, 1].abs()
