@@ -66,11 +66,12 @@ int make_map(const MapSpec& s, CUtensorMap* out) {
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < 5; ++i) { dims[i] = s.dim[i]; box[i] = s.box[i]; }
   for (int i = 0; i < 4; ++i) strides[i] = s.stride[i];
-  CUresult r = fn(out, s.tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.ptr, dims,
+  static const int exp_map = getenv("GC_EXP_MAP") ? atoi(getenv("GC_EXP_MAP")) : 0;   // experiment: 1 = plain FLOAT32 operand maps, 2 = no L2 promotion, 4 = 128B promotion
+  CUresult r = fn(out, (s.tf32 && !(exp_map & 1)) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s.ptr, dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   s.swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                  : (s.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  (exp_map & 2) ? CU_TENSOR_MAP_L2_PROMOTION_NONE : ((exp_map & 4) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return gc::fail((int)r,
@@ -120,10 +121,20 @@ struct Plan {
   dim3 grid;
   bool a_mn, b_mn;
   int b_bytes_override = 0;
+  bool pair = false;   // CTA-pair (cta_group::2) launch: 2-CTA clusters, B tile split between the CTAs
   Plan() { memset(&p, 0, sizeof(p)); p.e0 = p.e1 = p.f0 = p.g0 = p.g1 = 1; a_mn = b_mn = false; }
 };
 
 constexpr int kSmemBudget = 225 * 1024;
+
+// CTA-pair mode pays when the B tile is a large share of the per-k-iteration TMA rows (N >= 128) and needs an even
+// number of m-tiles (a pair works on m-tiles 2j, 2j+1 of the same n-tile) and the two-group bit-mask / plain epilogues.
+// An odd m-tile count is made even by the caller with one phantom tile row past the end of the outermost M dimension
+// (its TMA loads are zero-filled, its stores clipped, its bit-mask words skipped).
+bool pair_ok(long m_tiles, int bn, int epilogue, bool tma_mask) {
+  static const bool off = getenv("GC_NO_CTA2") != nullptr;
+  return !off && m_tiles >= 16 && bn >= 128 && bn % 32 == 0 && !(epilogue == EPI_MASK && tma_mask);
+}
 
 int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GemmParams& p = pl.p;
@@ -143,7 +154,7 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
                "%s: resident-B mode needs K-major B, one n-tile, <= 16 k-iterations of <= 4 taps", what);
   } else {
     p.b_slabs = 0; p.b_slab_bytes = 0;
-    p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : p.bn * 128;
+    p.b_bytes = pl.b_mn ? bpan * p.bk * 128 : (pl.pair ? p.bn / 2 : p.bn) * 128;
     if (pl.b_bytes_override) p.b_bytes = pl.b_bytes_override;
     p.b_bytes = (p.b_bytes + 1023) & ~1023;
   }
@@ -178,6 +189,11 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   GC_REQUIRE(total_tiles > 0 && total_tiles < (1L << 31), "%s: bad tile count", what);
   const dim3 grid((unsigned)std::min<long>(total_tiles, gc::kNumSMs), 1, 1);
   const size_t smem = (size_t)stages * stage + fixed;
+  if (pl.pair) {
+    GC_REQUIRE(!pl.a_mn && !pl.b_mn && p.ngroups == 0 && !p.b_resident && p.taps == 1 && total_tiles % 2 == 0 && p.mt % 2 == 0,
+               "%s: CTA-pair mode needs K-major operands, plain tiles and an even number of m-tiles", what);
+    p.pair = 1;
+  }
   auto launch = [&](auto kern) -> int {
     static thread_local const void* configured[3] = {nullptr, nullptr, nullptr};
     (void)configured;
@@ -190,17 +206,29 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
       cudaMemsetAsync(d_stats, 0, gc::kNumSMs * 16 * sizeof(long long), st);
       p.stats = d_stats;
     }
-    kern<<<grid, 320, smem, st>>>(p);
+    if (pl.pair) {   // 2-CTA clusters: CTAs (2c, 2c+1) form the pairs
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = grid; cfg.blockDim = dim3(320, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, kern, p);
+      if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaLaunchKernelEx (2-CTA clusters): %s", what, cudaGetErrorString(e));
+    } else {
+      kern<<<grid, 320, smem, st>>>(p);
+    }
     if (want_stats) {
       long long h[gc::kNumSMs * 16];
       cudaStreamSynchronize(st);
       cudaMemcpy(h, d_stats, sizeof(h), cudaMemcpyDeviceToHost);
       double m[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (unsigned c = 0; c < grid.x; ++c) for (int i = 0; i < 16; ++i) m[i] += (double)h[c * 16 + i] / grid.x;
-      fprintf(stderr, "[umma-stats] %-26s ctas=%u tiles/cta=%.1f k_iters=%d bn=%d stages=%d | clocks/cta total=%.0f prod_wait_empty=%.0f "
+      fprintf(stderr, "[umma-stats] %-26s %sctas=%u tiles/cta=%.1f k_iters=%d bn=%d stages=%d | clocks/cta total=%.0f prod_wait_empty=%.0f "
                       "mma_wait_full=%.0f mma_wait_tmem=%.0f epi0_wait_acc=%.0f epi1_wait_acc=%.0f epi0_total=%.0f | epi0 per panel (%.0f panels): free=%.0f ld=%.0f "
                       "math=%.0f sts+fence=%.0f bar=%.0f store=%.0f nbuf=%d\n",
-              what, grid.x, m[7], p.k_iters, p.bn, p.stages, m[5], m[0], m[1], m[2], m[3], m[4], m[6], m[12],
+              what, pl.pair ? "PAIR " : "", grid.x, m[7], p.k_iters, p.bn, p.stages, m[5], m[0], m[1], m[2], m[3], m[4], m[6], m[12],
               m[8] / std::max(1.0, m[12]), m[9] / std::max(1.0, m[12]), m[10] / std::max(1.0, m[12]), m[13] / std::max(1.0, m[12]), m[14] / std::max(1.0, m[12]), m[11] / std::max(1.0, m[12]), p.nbuf);
     }
     return gc::launch_status(what);
@@ -209,6 +237,7 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     GC_REQUIRE(pl.a_mn && pl.b_mn, "%s: slab mode needs MN-major operands", what);
     return launch(umma_gemm_kernel<true, true, true>);
   }
+  if (pl.pair) return launch(umma_gemm_kernel<false, false, false, true>);
   if (!pl.a_mn && !pl.b_mn) return launch(umma_gemm_kernel<false, false, false>);
   if (!pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<false, true, false>);
   if (pl.a_mn && pl.b_mn) return launch(umma_gemm_kernel<true, true, false>);
@@ -393,7 +422,7 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
   p.bk = 32;
   p.e0 = cdiv(g->OW, bx.ox);
   p.e1 = cdiv(g->OH, bx.oy);
-  const int e2 = cdiv(g->B, bx.b);
+  int e2 = cdiv(g->B, bx.b);
   p.f0 = cdiv(g->Cout, p.bn);
   p.g0 = g->KW * g->Cin / 32;
   p.g1 = g->KH;
@@ -402,14 +431,18 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
   if (int e = make_map(window_spec(g, x, bx), &p.mapA)) return e;
   p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[2][K1] = 1; p.a.mul[3][M1] = bx.oy; p.a.mul[4][M2] = bx.b;
   p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
+  pl.pair = pair_ok((long)p.e0 * p.e1 * e2, p.bn, epilogue, mask_bits == nullptr);
+  if (pl.pair && ((long)p.e0 * p.e1 * e2) % 2) e2 += 1;   // phantom batch tile
+  const int b_rows = pl.pair ? p.bn / 2 : p.bn;   // CTA-pair mode: each CTA stages half of the weight tile
   // B: weights [Cout][K]
   {
     const uint64_t dim[2] = {(uint64_t)K, (uint64_t)g->Cout}, str[2] = {1, (uint64_t)K};
-    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    const uint32_t box[2] = {32, (uint32_t)b_rows};
     if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
   }
   p.b.mul[0][K0] = 32; p.b.mul[0][K1] = 32 * p.g0; p.b.mul[1][N0] = p.bn;
-  p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  p.b_panels = 1; p.b_panel_bytes = b_rows * 128;
+  p.pair_b_dim = 1; p.pair_b_off = b_rows;
   // D (+ mask source with the same geometry)
   const int inner = std::min(32, p.bn);
   if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
@@ -513,7 +546,7 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
   p.bk = 32;
   p.e0 = cdiv(NI, bx.ox);
   p.e1 = cdiv(NJ, bx.oy);
-  const int e2 = cdiv(g->B, bx.b);
+  int e2 = cdiv(g->B, bx.b);
   p.f0 = Ntot / p.bn;
   p.g0 = g->Cout / 32;
   p.g1 = TB;
@@ -523,15 +556,19 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
   p.a.mul[0][K0] = 32; p.a.mul[1][M0] = bx.ox; p.a.mul[1][K1] = -1; p.a.mul[2][M1] = bx.oy; p.a.mul[2][K2] = -1;
   p.a.mul[3][M2] = bx.b;
   p.a_panels = 1; p.a_panel_bytes = bx.ox * bx.oy * bx.b * 128;
+  pl.pair = pair_ok((long)p.e0 * p.e1 * e2, p.bn, want_mask ? EPI_MASK : EPI_STORE, mask_bits == nullptr);
+  if (pl.pair && ((long)p.e0 * p.e1 * e2) % 2) e2 += 1;   // phantom batch tile
+  const int b_rows = pl.pair ? p.bn / 2 : p.bn;   // CTA-pair mode: each CTA stages half of the weight tile
   // B: wd viewed as [ncls*Cin][Kd], k = (a*TB + b')*Cout + n
   {
     const uint64_t dim[2] = {(uint64_t)Kd, (uint64_t)Ntot};
     const uint64_t str[2] = {1, (uint64_t)Kd};
-    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    const uint32_t box[2] = {32, (uint32_t)b_rows};
     if (int e = make_map(spec(wd, 2, dim, str, box, 1, 1), &p.mapB)) return e;
   }
   p.b.mul[0][K0] = 32; p.b.mul[0][K1] = g->Cout; p.b.mul[0][K2] = TB * g->Cout; p.b.mul[1][N0] = p.bn;
-  p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  p.b_panels = 1; p.b_panel_bytes = b_rows * 128;
+  p.pair_b_dim = 1; p.pair_b_off = b_rows;
   // D / mask: one strided map per parity class over dx[B][Hp][Wp][Cin]
   const int inner = std::min(32, g->Cin);
   for (int py = 0; py < g->S; ++py) {
@@ -768,12 +805,16 @@ int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const floa
       }
     }
   }
+  pl.pair = getenv("GC_EXP") == nullptr && pair_ok(p.e0, p.bn, epilogue, false);
+  if (pl.pair && p.e0 % 2) p.e0 += 1;   // phantom row tile
+  const int b_rows = pl.pair ? p.bn / 2 : p.bn;   // CTA-pair mode: each CTA stages half of the weight tile
   {
     const uint64_t dim[2] = {(uint64_t)K, (uint64_t)N}, str[2] = {1, (uint64_t)ldw};
-    const uint32_t box[2] = {32, (uint32_t)p.bn};
+    const uint32_t box[2] = {32, (uint32_t)b_rows};
     if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
   }
-  p.b.mul[0][K0] = 32; p.b.mul[1][N0] = p.bn; p.b_panels = 1; p.b_panel_bytes = p.bn * 128;
+  p.b.mul[0][K0] = 32; p.b.mul[1][N0] = p.bn; p.b_panels = 1; p.b_panel_bytes = b_rows * 128;
+  p.pair_b_dim = 1; p.pair_b_off = b_rows;
   {
     const int inner = std::min(32, p.bn);
     const uint64_t dim[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)splits}, str[3] = {1, (uint64_t)ldy, (uint64_t)ldy * M};

@@ -56,6 +56,8 @@ struct alignas(64) GemmParams {
   int cpm_shift;       // log2(cols_per_map)
   int exp_a_off, exp_a_sbo, exp_a_baseoff;  // bring-up experiment hooks for the A descriptor (0 = normal)
   int exp_b_off, exp_b_lbo;                 // same for the B descriptor (MN-major shifted-view experiments)
+  int pair;                                 // 1: CTA-pair mode (cta_group::2, see the kernel)
+  int pair_b_dim, pair_b_off;               // B tensor-map coordinate that selects the second CTA's half of the B tile
   // patch mode: one TMA-loaded input patch per stage serves `taps` shifted A views (convolution taps); B (the whole
   // weight matrix) is loaded once per CTA and stays resident in shared memory.
   int taps;             // MMA groups per stage (1 = plain GEMM)

@@ -51,6 +51,45 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: the pair's leader is the even CTA of the 2-CTA cluster ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are accounted on the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, const int (&c)[5]) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(leader_bar), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrive (when all prior MMAs of this thread retire) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, const int (&c)[5]) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
                ::"l"((uint64_t)map), "r"(src), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4])
@@ -232,7 +271,14 @@ __device__ __forceinline__ void k_deltas(const TmaAddr& t, int g0, int g1, int (
 //              per 128x32 tile on one group, ncu: profiles/r01_ncu_conv1_fprop_details.txt), so two groups in
 //              ping-pong double its throughput; with TMA-loaded mask tiles (EPI_MASK without bit masks) only group 0 runs.
 // The epilogue of tile i overlaps the mainloop of tile i+1 and barrier/TMEM set-up is paid once per SM.
-template <bool A_MN, bool B_MN, bool SLAB>
+// CTA2: the CTAs of a 2-CTA cluster work as a pair on a 256 x N tile (tcgen05 cta_group::2): each stages its own 128 rows
+// of A and HALF of the B tile, the leader (even CTA) issues M=256 MMAs that read both halves, each CTA's TMEM receives
+// its 128 accumulator rows and each CTA runs its own epilogue.  TMA requests per CTA and k-iteration drop from 128 + N
+// rows to 128 + N/2 - the per-SM TMA row rate (~0.5 x 128 B rows per clock) is what bounds the large layers
+// (profiles/r01_operand_skip_experiment.txt).  Barriers: `full` lives in the leader and collects the bytes of both CTAs;
+// `empty` / `tmem_full` are signalled in both CTAs by multicast commits; the leader's `tmem_empty` counts the epilogue
+// warps of both CTAs.
+template <bool A_MN, bool B_MN, bool SLAB, bool CTA2 = false>
 __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -254,6 +300,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   const int acc_cols = ((p.bn + 31) >> 5) << 5;
   const int acc_stages = p.acc_stages;
   const bool timed = p.stats != nullptr;
+  const uint32_t pair_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -262,7 +309,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
+      mbar_init(tempty0 + 8 * a, CTA2 ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int q = 0; q < 4; ++q) mbar_init(aux0 + 8 * q, 1);
     mbar_init(bres_bar, 1);
@@ -270,16 +317,24 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     fence_async_smem();
   }
   if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if ((p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) && p.nt * p.bn <= 512) {
     for (int i = threadIdx.x; i < p.nt * p.bn; i += blockDim.x) s_bias[i] = i < p.n_total ? __ldg(p.bias + i) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -325,31 +380,49 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         for (int d = 0; d < 5; ++d) { ca[d] = p.a.off[d]; cb[d] = p.b.off[d]; }
         coords(p.a, src, 0, kSrc, ca);
         coords(p.b, src, 0, kSrc, cb);
+        if constexpr (CTA2) {   // this CTA's half of the B tile
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cb[d] += (d == p.pair_b_dim) ? (int)pair_rank * p.pair_b_off : 0;
+        }
         for (int k = 0; k < k_iters; ++k) {
           mbar_wait_t(empty0 + 8 * s, ph ^ 1, timed, w_empty);
-          mbar_expect_tx(full0 + 8 * s, tx);
-          const uint32_t sa = smem_u32(smem) + (uint32_t)s * (uint32_t)stage_bytes, sb = sa + p.a_bytes;
-          // panels are walked incrementally (no div/mod on the single producer thread's critical path)
-          int cq[5];
-#pragma unroll
-          for (int d = 0; d < 5; ++d) cq[d] = ca[d];
-          for (int q = 0; q < a_panels; ++q) {
-            tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full0 + 8 * s, cq);
-#pragma unroll
-            for (int d = 0; d < 5; ++d) cq[d] += pa[d];
+          const uint32_t full_s = CTA2 ? mapa_rank(full0 + 8 * s, 0) : full0 + 8 * s;   // pair mode: the leader's barrier
+          if constexpr (CTA2) {
+            if (pair_rank == 0) mbar_expect_tx(full0 + 8 * s, 2u * tx);   // the bytes of both CTAs land on the leader's barrier
+          } else {
+            mbar_expect_tx(full0 + 8 * s, tx);
           }
+          const uint32_t sa = smem_u32(smem) + (uint32_t)s * (uint32_t)stage_bytes, sb = sa + p.a_bytes;
+          if (a_panels == 1 && b_panels <= 1) {   // the common case, straight-line (the panel loops below unroll badly)
+            if constexpr (CTA2) tma_load_5d_pair(sa, &p.mapA, full_s, ca); else tma_load_5d(sa, &p.mapA, full_s, ca);
+            if (b_panels == 1) {
+              if constexpr (CTA2) tma_load_5d_pair(sb, &p.mapB, full_s, cb); else tma_load_5d(sb, &p.mapB, full_s, cb);
+            }
+          } else {
+            // panels are walked incrementally (no div/mod on the single producer thread's critical path)
+            int cq[5];
 #pragma unroll
-          for (int d = 0; d < 5; ++d) cq[d] = cb[d];
-          int q1 = 0;
-          for (int q = 0; q < b_panels; ++q) {
-            tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full0 + 8 * s, cq);
-            if (++q1 == b_period) {
-              q1 = 0;
+            for (int d = 0; d < 5; ++d) cq[d] = ca[d];
+#pragma unroll 1
+            for (int q = 0; q < a_panels; ++q) {
+              tma_load_5d(sa + q * p.a_panel_bytes, &p.mapA, full_s, cq);
 #pragma unroll
-              for (int d = 0; d < 5; ++d) cq[d] += pb2[d];
-            } else {
+              for (int d = 0; d < 5; ++d) cq[d] += pa[d];
+            }
 #pragma unroll
-              for (int d = 0; d < 5; ++d) cq[d] += pb[d];
+            for (int d = 0; d < 5; ++d) cq[d] = cb[d];
+            int q1 = 0;
+#pragma unroll 1
+            for (int q = 0; q < b_panels; ++q) {
+              tma_load_5d(sb + q * p.b_panel_bytes, &p.mapB, full_s, cq);
+              if (++q1 == b_period) {
+                q1 = 0;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) cq[d] += pb2[d];
+              } else {
+#pragma unroll
+                for (int d = 0; d < 5; ++d) cq[d] += pb[d];
+              }
             }
           }
           // next k-iteration: (k0, k1, k2) advance as mixed-radix digits, the coordinates by the matching increments
@@ -374,10 +447,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     }
     __syncwarp();
   } else if (warp == 9) {
-    if (elect_one()) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4
+    if (pair_rank == 0 && elect_one()) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) | ((128u >> 4) << 24);
+                             ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
       const int ksteps = p.bk >> 3;
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
       const uint32_t b_lbo = p.exp_b_lbo ? (uint32_t)p.exp_b_lbo : (B_MN ? (uint32_t)p.b_panel_bytes : 0u);
@@ -458,7 +531,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
             } else {
               const uint32_t alo = a_lo_base + ((sa + a_off0) >> 4);
               const uint32_t blo = b_lo_base + ((sb + b_off) >> 4);
-              if (ksteps == 4) {
+              if constexpr (CTA2) {
+                for (int ks = 0; ks < ksteps; ++ks)
+                  umma_tf32_pair(tacc, mk64(alo + ks * a_step, a_hi), mk64(blo + ks * b_step, b_hi), idesc, (k | ks) ? 1u : 0u);
+              } else if (ksteps == 4) {
                 umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, k ? 1u : 0u);
                 umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
                 umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
@@ -469,10 +545,12 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
               }
             }
           }
-          umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+          if constexpr (CTA2) umma_commit_pair(empty0 + 8 * s);   // frees the stage in both CTAs
+          else umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
           if (++s == stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull0 + 8 * acc);
+        if constexpr (CTA2) umma_commit_pair(tfull0 + 8 * acc);
+        else umma_commit(tfull0 + 8 * acc);
         if (++acc == acc_stages) { acc = 0; aph ^= 1; }
       }
       if (timed) {
@@ -618,7 +696,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         if (q == n_panels - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+          if (lane == 0) {
+            if constexpr (CTA2) mbar_arrive_cluster(mapa_rank(tempty0 + 8 * acc, 0));   // the leader issues the pair's MMAs
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+          }
         }
         const int col0 = n_tile * p.bn + q * 32;
         unsigned bits_w = 0u;
@@ -706,9 +787,15 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still signal / read it
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    } else {
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+    }
   }
 }
 
