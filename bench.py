@@ -509,6 +509,25 @@ def run_b200(args):
                                **({"hbm_gbs": v[3] / v[1] / 1e9, "hbm_frac": v[3] / v[1] / 1e9 / pk["hbm"]} if v[3] else {}))
                        for k, v in by.items()}}
 
+    if rank == 0 and world == 1:
+        # yardstick only (not on any product path): what cuBLAS sustains with TF32 inputs on this box, since
+        # MEASURED_PEAKS.json has no TF32 entry and 1/2 x (sustained bf16) is an assumption
+        try:
+            old = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            a_ = torch.randn(8192, 8192, device=dev); b_ = torch.randn(8192, 8192, device=dev)
+            for _ in range(3):
+                torch.matmul(a_, b_)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(40):
+                torch.matmul(a_, b_)
+            e1.record(); torch.cuda.synchronize()
+            roof["tf32_cublas_sustained_tflops"] = 40 * 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            torch.backends.cuda.matmul.allow_tf32 = old
+            del a_, b_
+        except Exception as ex:   # pragma: no cover
+            roof["tf32_cublas_sustained_tflops"] = None
     if rank == 0:
         hbm = hbm_microbench(A, dev, pk) if world == 1 else None
         cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None

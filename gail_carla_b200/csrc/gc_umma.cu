@@ -666,6 +666,7 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
     pl.a_mn = pl.b_mn = true;
     const int C = g->Cin, KC = 4 * C;
     p.bn = 512; p.mma_n = 64; p.acc_stages = 1; p.ngroups = 8;
+    if (g->Cout <= 64 && getenv("GC_NO_M64") == nullptr) p.mma_m = 64;
     p.bk = sg.R;
     p.e0 = cdiv(g->Cout, 128); p.e1 = 1;
     p.f0 = C / 32;                              // n-tile = 32-channel chunk
@@ -727,6 +728,7 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
   int ky_per, n_tiles;
   wgrad_tile_n(g, p.bn, ky_per, n_tiles);
   GC_REQUIRE(KC % 32 == 0 && (KC >= 256 ? KC % 256 == 0 : true), "gc_conv_wgrad: unsupported KW*Cin=%d", KC);
+  if (g->Cout <= 64 && getenv("GC_NO_M64") == nullptr) p.mma_m = 64;
   const PixBox bx = choose_box(g->OW, g->OH, g->B, wgrad_max_rows(p.bn), 8, 4.0);
   p.bk = bx.ox * bx.oy * bx.b;
   p.e0 = cdiv(g->Cout, 128);

@@ -72,6 +72,9 @@ struct alignas(64) GemmParams {
   int grp_b_off[16];        // byte offset of each group's B view inside the stage's B region
   int grp_acc[16];          // TMEM column offset of each group's accumulator block
   int mma_n;                // N of one MMA (0 = bn)
+  int mma_m;                // M of one MMA: 0 / 128, or 64 when the problem has <= 64 rows (wgrad with Cout <= 64): the SS-mode
+                            // MMA is bound by its shared-memory operand reads, and a 64-row A tile halves A's share.
+                            // TMEM rows then sit in lanes 0-15 of each 32-lane quarter (row = 16*quarter + lane)
   int acc_stages;           // TMEM accumulator stages: 2, or 1 when bn > 256
   int panel_tab0[16], panel_tab1[16];  // slab mode: output panel q -> added to output coordinates 0 and 1
   // LeakyReLU' bitmask (1 bit per fp32 element of an activation tensor, same linear order): written by the

@@ -450,7 +450,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     if (pair_rank == 0 && elect_one()) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, majors, N>>3, M>>4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) | (((CTA2 ? 256u : 128u) >> 4) << 24);
+                             ((uint32_t)((p.mma_n ? p.mma_n : p.bn) >> 3) << 17) |
+                             (((CTA2 ? 256u : (p.mma_m == 64 ? 64u : 128u)) >> 4) << 24);
       const int ksteps = p.bk >> 3;
       const uint32_t a_lbo = A_MN ? (uint32_t)p.a_panel_bytes : 0u;
       const uint32_t b_lbo = p.exp_b_lbo ? (uint32_t)p.exp_b_lbo : (B_MN ? (uint32_t)p.b_panel_bytes : 0u);
@@ -567,7 +568,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     // of this CTA).  With EPI_MASK the panel's LeakyReLU' source tile (same box geometry as the output) is
     // TMA-loaded into the staging buffer two panels ahead, multiplied in place and stored from the same buffer.
     const int grp = warp >> 2, wq = warp & 3;      // epilogue group, TMEM lane quarter
-    const int row = wq * 32 + lane;
+    const bool m64 = p.mma_m == 64;                // M = 64 accumulators: 16 rows per lane quarter, in its lanes 0-15
+    const int row = m64 ? wq * 16 + lane : wq * 32 + lane;
+    const bool row_live = !m64 || lane < 16;
     // the group's TMA traffic is issued by the elected lane of its first warp (elect.sync picks the same lane every time,
     // so bulk-group waits see the stores that lane committed)
     auto leader = [&]() -> bool { return wq == 0 && elect_one(); };
@@ -634,6 +637,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const float slope = p.slope;
     const bool bias_smem = p.nt * p.bn <= 512;
     const bool want_bits = p.bits_out != nullptr && epi == EPI_BIAS_LRELU;
+    // fprop tiles: consecutive panels are consecutive 32-channel groups of the same pixels, i.e. consecutive bit words -
+    // the word index and the clipping test are then formed once per tile instead of once per panel
+    const bool simple_panels = !SLAB && p.cols_per_map == 0 && p.d.period == 0 && p.d.panel[0] == 32 && p.d.panel[1] == 0 &&
+                               p.d.panel[2] == 0 && p.d.panel[3] == 0 && p.d.panel[4] == 0;
     const uint32_t s_bias_u32 = smem_u32(s_bias), my_staging_u32 = smem_u32(my_staging);
     int pc = 0, bi = 0;            // panels done so far, staging buffer of the current panel (pc % nbuf without the division)
     uint32_t bph = 0;              // (pc / nbuf) & 1
@@ -659,6 +666,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         const long base = mi == 0 ? bbase0 : p.bit_base[mi];
         return (base + cq[1] * bs0 + cq[2] * bs1 + cq[3] * bs2 + cq[0] + thread_bit_off) >> 5;
       };
+      const long bw0 = (want_bits && simple_panels) ? bit_word(0) : -1;
       unsigned mbits[8];
       if (bitmask) {  // issued before waiting for the accumulator: the loads overlap the tile's mainloop
 #pragma unroll
@@ -721,13 +729,21 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           }
         }
         if (want_bits) {
-          unsigned w4[4] = {0u, 0u, 0u, 0u};   // four short OR chains instead of one 32-deep dependency chain
+          // bit j = (v[j] > 0), formed without predicates: for the float's bits x as a signed int, x > 0  <=>  the
+          // sign bit of (~x & -x); a funnel shift moves that bit into the word.  Four independent 8-deep chains.
+          unsigned w4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w4[j & 3] |= v[j] > 0.f ? (1u << j) : 0u;
-          unsigned w = (w4[0] | w4[1]) | (w4[2] | w4[3]);
+          for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int j = 7; j >= 0; --j) {
+              const int x = __float_as_int(v[8 * c + j]);
+              w4[c] = __funnelshift_l((unsigned)(~x & -x), w4[c], 1);
+            }
+          }
+          unsigned w = (w4[0] | (w4[1] << 8)) | ((w4[2] << 16) | (w4[3] << 24));
           if (col0 + 32 > p.n_total) w &= (1u << (p.n_total - col0)) - 1u;   // partial last panel
           bits_w = w;
-          bits_wi = bit_word(q);
+          bits_wi = simple_panels ? (bw0 >= 0 ? bw0 + q : -1) : bit_word(q);
         }
         if (bitmask) {
           unsigned w = 0u;
@@ -752,7 +768,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         const long long c2a = timed ? clock64() : 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (j < nchunk) sts128(buf + soff[j], v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (j < nchunk && row_live) sts128(buf + soff[j], v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         fence_async_smem();
         const long long c2b = timed ? clock64() : 0;

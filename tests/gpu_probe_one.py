@@ -11,7 +11,8 @@ nw = 2048 if layer == 1 else cout * cin * 16
 x = torch.randn(B * g.in_batch_stride, device="cuda"); y = torch.randn(B * g.out_batch_stride, device="cuda")
 dx = torch.zeros_like(x); w = torch.randn(nw, device="cuda") * 0.05; bias = torch.zeros(cout, device="cuda")
 z = A.conv_wgrad_splits(g); part = torch.zeros(z * nw, device="cuda")
-fn = {"fprop": lambda: A.conv_fprop(g, x, w, bias, y, A.EPI_BIAS_LRELU, 0.2),
+bits = torch.zeros(y.numel() // 32, dtype=torch.int32, device="cuda") if os.environ.get("BITS") else None
+fn = {"fprop": lambda: A.conv_fprop(g, x, w, bias, y, A.EPI_BIAS_LRELU, 0.2, mask_bits=bits),
       "dgrad": lambda: A.conv_dgrad(g, y, w, dx, None, 0.2),
       "wgrad": lambda: A.conv_wgrad(g, y, x, part, z)}[op]
 for _ in range(reps):
