@@ -287,8 +287,20 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL's version banner)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created; stdout must carry only the JSON
+        # line, so file descriptor 1 points at stderr while the process group and its first collective are set up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     A.load_library()
     prof = Profiler(A)
     pk = peaks()
@@ -509,6 +521,7 @@ def run_b200(args):
                                **({"hbm_gbs": v[3] / v[1] / 1e9, "hbm_frac": v[3] / v[1] / 1e9 / pk["hbm"]} if v[3] else {}))
                        for k, v in by.items()}}
 
+    hbm = hbm_microbench(A, dev, pk) if (rank == 0 and world == 1) else None   # before the power-hungry GEMM yardstick
     if rank == 0 and world == 1:
         # yardstick only (not on any product path): what cuBLAS sustains with TF32 inputs on this box, since
         # MEASURED_PEAKS.json has no TF32 entry and 1/2 x (sustained bf16) is an assumption
@@ -529,7 +542,6 @@ def run_b200(args):
         except Exception as ex:   # pragma: no cover
             roof["tf32_cublas_sustained_tflops"] = None
     if rank == 0:
-        hbm = hbm_microbench(A, dev, pk) if world == 1 else None
         cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
         line = {"metric": "ppo_wdgail_update_env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
