@@ -234,16 +234,53 @@ __device__ __forceinline__ void walk_init(TileWalk& w, const GemmParams& p, int 
   w.tile = start;
   w.tstep = step;
 }
-__device__ __forceinline__ void walk_next(TileWalk& w) {
+// returns the carries out of digits 0..4 as a bit mask
+__device__ __forceinline__ unsigned walk_next(TileWalk& w) {
   int c = 0;
+  unsigned carries = 0u;
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     const int v = w.dig[i] + w.step[i] + c;
     c = v >= w.rad[i] ? 1 : 0;
+    carries |= (unsigned)c << i;
     w.dig[i] = c ? v - w.rad[i] : v;
   }
   w.dig[5] += w.step[5] + c;
   w.tile += w.tstep;
+  return carries;
+}
+
+// Tile-level TMA coordinates of one operand / output kept in registers and advanced together with the digits: the
+// coordinates are linear in the digits, so a step adds a constant vector plus one correction vector per carry.  The
+// per-tile recomputation (30 multiply-adds fed by constant-bank loads) was ~1000 of the ~2300 clocks the producer and the
+// epilogue spent per 128x32 conv1 tile.
+struct CoordTrack {
+  int c[5], base[5], corr[5][5];
+};
+__device__ __forceinline__ void track_init(CoordTrack& t, const TmaAddr& a, const TileWalk& w) {
+  constexpr int kDigitSrc[6] = {M0, M1, M2, N0, N1, Z};
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    int c = a.off[d], b = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      c += a.mul[d][kDigitSrc[i]] * w.dig[i];
+      b += a.mul[d][kDigitSrc[i]] * w.step[i];
+    }
+    t.c[d] = c;
+    t.base[d] = b;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) t.corr[i][d] = a.mul[d][kDigitSrc[i + 1]] - w.rad[i] * a.mul[d][kDigitSrc[i]];
+  }
+}
+__device__ __forceinline__ void track_next(CoordTrack& t, unsigned carries) {
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    int v = t.c[d] + t.base[d];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v += ((carries >> i) & 1u) ? t.corr[i][d] : 0;
+    t.c[d] = v;
+  }
 }
 __device__ __forceinline__ void walk_src(const TileWalk& w, const GemmParams& p, int (&src)[kSrc], int& n_tile) {
   src[M0] = w.dig[0]; src[M1] = w.dig[1]; src[M2] = w.dig[2];
@@ -365,7 +402,11 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       }
       TileWalk w;
       walk_init(w, p, blockIdx.x, gridDim.x);
-      for (; w.tile < total_tiles; walk_next(w)) {
+      const bool tracked = p.kz_stride == 0;   // split-K tiles start at a z-dependent k-iteration: computed per tile
+      CoordTrack ta_, tb_;
+      track_init(ta_, p.a, w);
+      track_init(tb_, p.b, w);
+      for (; w.tile < total_tiles;) {
         int src[kSrc], n_tile, ca[5], cb[5];
         walk_src(w, p, src, n_tile);
         int k0 = 0, k1 = 0;
@@ -376,10 +417,15 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           k1 = t % g1;
           src[K0] = k0; src[K1] = k1; src[K2] = t / g1;
         }
+        if (tracked) {
 #pragma unroll
-        for (int d = 0; d < 5; ++d) { ca[d] = p.a.off[d]; cb[d] = p.b.off[d]; }
-        coords(p.a, src, 0, kSrc, ca);
-        coords(p.b, src, 0, kSrc, cb);
+          for (int d = 0; d < 5; ++d) { ca[d] = ta_.c[d]; cb[d] = tb_.c[d]; }
+        } else {
+#pragma unroll
+          for (int d = 0; d < 5; ++d) { ca[d] = p.a.off[d]; cb[d] = p.b.off[d]; }
+          coords(p.a, src, 0, kSrc, ca);
+          coords(p.b, src, 0, kSrc, cb);
+        }
         if constexpr (CTA2) {   // this CTA's half of the B tile
 #pragma unroll
           for (int d = 0; d < 5; ++d) cb[d] += (d == p.pair_b_dim) ? (int)pair_rank * p.pair_b_off : 0;
@@ -442,6 +488,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           }
           if (++s == stages) { s = 0; ph ^= 1; }
         }
+        const unsigned carries = walk_next(w);
+        track_next(ta_, carries);
+        track_next(tb_, carries);
       }
       if (timed) p.stats[blockIdx.x * 16 + 0] = w_empty;
     }
@@ -650,10 +699,13 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     walk_init(w, p, active ? (int)blockIdx.x + (two_groups ? grp * (int)gridDim.x : 0) : total_tiles, tile_step);
     int acc = two_groups ? grp : 0;   // accumulator stage drained by this group for the current tile, and its phase
     uint32_t aph = 0;
-    for (; w.tile < total_tiles; walk_next(w)) {
+    CoordTrack td_;
+    track_init(td_, p.d, w);
+    for (; w.tile < total_tiles; track_next(td_, walk_next(w))) {
       int src[kSrc], n_tile, cd[5];
       walk_src(w, p, src, n_tile);
-      tile_coords(p.d, src, cd);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) cd[d] = td_.c[d];
       // 32-bit word (in the bit tensor of the activation the mask describes) of this thread's row in panel q, or -1 if the
       // row is clipped.  Strides / extents of map 0 live in registers (hoisted above the tile loop).
       auto bit_word = [&](int q) -> long {
