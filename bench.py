@@ -415,6 +415,8 @@ def run_b200(args):
             return len(self.inner)
         def __iter__(self):
             for k, batch in enumerate(self.inner):
+                # 15 of the 24 chunks ride along with the expert batches, the other 9 go up under rewards + PPO (measured:
+                # moving more of them behind the discriminator epochs does not help and slows the expert-resident variant)
                 if double and k > 0 and state["chunk"] < NCH - 8:
                     enqueue_chunks((state["i"] + 1) % 2, state["chunk"] + 1)
                 yield batch
