@@ -41,6 +41,8 @@ CONFIGS = {
     # the per-rank share of c4 at 8 GPUs (8 envs, 512-row minibatches) on one GPU: isolates launch / host overheads
     "c4r8": dict(T=1024, N=8, B_ppo=512, B_gail=512, ppo_epoch=1, gail_epoch=1,
                  workload="per-rank share of configs[3] at 8 GPUs: 8 envs x 1024 steps, B=512"),
+    "c4r4": dict(T=1024, N=16, B_ppo=1024, B_gail=1024, ppo_epoch=1, gail_epoch=1,
+                 workload="per-rank share of configs[3] at 4 GPUs: 16 envs x 1024 steps, B=1024"),
     "tiny": dict(T=64, N=8, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1, workload="tiny: 8 envs x 64 steps, B=128"),
     # the bounded sample the CPU arm runs: configs[0] verbatim
     "c1": dict(T=128, N=1, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1,
