@@ -149,7 +149,7 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
   const int bpan = (p.bn + 31) / 32;
   if (p.b_resident) {
     p.b_bytes = 0;
-    p.b_slab_bytes = p.bn * 128;
+    p.b_slab_bytes = (p.mma_n ? p.mma_n : p.bn) * 128;
     GC_REQUIRE(!pl.b_mn && pl.grid.y == 1 && p.k_iters <= 16 && p.taps <= 4 && p.bk == 32,
                "%s: resident-B mode needs K-major B, one n-tile, <= 16 k-iterations of <= 4 taps", what);
   } else {
@@ -382,35 +382,49 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
   if (g->S == 1 && g->KH == 2 && g->KW == 2 && g->Cin == 16 && g->Cout <= 256 && g->OW >= 32 && getenv("GC_NO_PATCH") == nullptr) {
     Plan pl;
     GemmParams& p = pl.p;
-    const PixBox bx{32, 4, 1};
-    p.bn = g->Cout;
+    // Two 32x4-pixel sub-tiles per tile when Cout == 32 (one 32x9-row patch, two accumulator blocks, two output panels):
+    // the per-tile bookkeeping of all three roles - as large as the work itself for a 128x32 tile - is paid half as often.
+    const int subs = (g->Cout == 32 && getenv("GC_NO_SUBTILES") == nullptr) ? 2 : 1;
+    const PixBox pbx{32, 4, 1};                  // one output panel (= one sub-tile)
+    p.bn = subs * g->Cout;
+    p.mma_n = g->Cout;
     p.bk = 32;
-    p.e0 = cdiv(g->OW, 32); p.e1 = cdiv(g->OH, 4);
+    p.e0 = cdiv(g->OW, 32); p.e1 = cdiv(g->OH, 4 * subs);
     p.k_iters = 1;
     {
       const uint64_t dim[4] = {32, (uint64_t)g->OW, (uint64_t)g->H, (uint64_t)g->B};
       const uint64_t str[4] = {1, (uint64_t)g->Cin, (uint64_t)g->Wp * g->Cin, (uint64_t)g->in_batch_stride};
-      const uint32_t box[4] = {32, 32, 5, 1};
+      const uint32_t box[4] = {32, 32, (uint32_t)(4 * subs + 1), 1};
       if (int e = make_map(spec(x, 4, dim, str, box, 1, 1), &p.mapA)) return e;
     }
-    p.a.mul[1][M0] = 32; p.a.mul[2][M1] = 4; p.a.mul[3][M2] = 1;
-    p.a_panels = 1; p.a_panel_bytes = 32 * 5 * 128; p.a_bytes = 20480;
-    p.taps = 2; p.tap_off[0] = 0; p.tap_off[1] = 32 * 128;
-    p.b_tab[0] = 0; p.b_tab[1] = 1;
+    p.a.mul[1][M0] = 32; p.a.mul[2][M1] = 4 * subs; p.a.mul[3][M2] = 1;
+    p.a_panels = 1; p.a_panel_bytes = 32 * (4 * subs + 1) * 128; p.a_bytes = (p.a_panel_bytes + 1023) & ~1023;
+    p.taps = 2 * subs;
+    for (int sub = 0; sub < subs; ++sub) for (int ky = 0; ky < 2; ++ky) {
+      const int t = sub * 2 + ky;
+      p.tap_off[t] = (sub * 4 + ky) * 32 * 128;   // rows (4*sub + ky .. +3) of the patch
+      p.b_tab[t] = (unsigned char)ky;
+      p.tap_acc[t] = sub * g->Cout;
+      if (ky == 0) p.tap_fresh |= 1 << t;
+    }
     {
       const uint64_t dim[2] = {64, (uint64_t)g->Cout}, str[2] = {1, 64};
-      const uint32_t box[2] = {32, (uint32_t)p.bn};
+      const uint32_t box[2] = {32, (uint32_t)g->Cout};
       if (int e = make_map(spec(w, 2, dim, str, box, 1, 1), &p.mapB)) return e;
     }
     p.b_resident = 1; p.b_slabs = 2;
-    const int inner = std::min(32, p.bn);
-    if (int e = make_map(out_spec(g, y, bx, inner, 0, p.bn >= 32), &p.mapD[0])) return e;
-    if (epilogue == EPI_MASK && !mask_bits) { if (int e = make_map(out_spec(g, mask_src, bx, inner, 0, p.bn >= 32), &p.mapX[0])) return e; }
+    const int inner = std::min(32, g->Cout);
+    if (int e = make_map(out_spec(g, y, pbx, inner, 0, g->Cout >= 32), &p.mapD[0])) return e;
+    if (epilogue == EPI_MASK && !mask_bits) { if (int e = make_map(out_spec(g, mask_src, pbx, inner, 0, g->Cout >= 32), &p.mapX[0])) return e; }
     else p.mapX[0] = p.mapD[0];
-    p.d.mul[1][M0] = 32; p.d.mul[2][M1] = 4; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
+    p.d.mul[1][M0] = 32; p.d.mul[2][M1] = 4 * subs; p.d.mul[3][M2] = 1; p.d.panel[0] = 32;
+    if (subs > 1) {   // panel q = sub-tile q / sub_panels, channel panel q % sub_panels
+      p.sub_panels = (g->Cout + 31) / 32;
+      p.d.period = p.sub_panels; p.d.panel2[2] = 4;
+    }
     p.d_box_bytes = inner * 4 * 128;
     p.epilogue = epilogue; p.slope = slope; p.bias = bias; p.n_total = g->Cout;
-    set_bits(p, bx);
+    set_bits(p, pbx);
     pl.grid = dim3(p.e0 * p.e1 * g->B, 1, 1);
     return finish_and_launch(pl, (cudaStream_t)stream, "gc_conv_fprop(row-patch)");
   }

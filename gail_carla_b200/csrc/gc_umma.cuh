@@ -62,6 +62,10 @@ struct alignas(64) GemmParams {
   // weight matrix) is loaded once per CTA and stays resident in shared memory.
   int taps;             // MMA groups per stage (1 = plain GEMM)
   int tap_off[4];       // byte offset of each tap's A view inside the stage
+  int tap_acc[4];       // TMEM column offset of the accumulator block each tap adds to (sub-tiles of one staged patch)
+  int tap_fresh;        // bit t: tap t is the first contribution to its accumulator block (0 = only tap 0)
+  int sub_panels;       // > 0: the tile's 32-column panels are `sub_panels` channel panels per sub-tile, sub-tile after
+                        // sub-tile (bias / channel index of panel q = (q % sub_panels) * 32); 0 = panels are channel panels
   int b_resident;       // 1: B slabs are loaded once per CTA
   int b_slabs;          // resident 32-wide K slabs
   int b_slab_bytes;     // bn * 128

@@ -525,9 +525,14 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         gb[g] = SLAB ? b_lo_base + ((uint32_t)p.grp_b_off[g] >> 4) : 0u;
         ga[g] = SLAB ? (uint32_t)p.grp_acc[g] : 0u;
       }
-      uint32_t ta[4];   // per-tap A descriptor constants (taps are shifted views of one staged patch)
+      uint32_t ta[4], tacc_off[4];   // per-tap A descriptor constants (taps are shifted views of one staged patch) and
+                                     // accumulator column blocks (sub-tiles of the patch)
 #pragma unroll
-      for (int t = 0; t < 4; ++t) ta[t] = a_lo_base + ((a_off0 + (uint32_t)p.tap_off[t]) >> 4);
+      for (int t = 0; t < 4; ++t) {
+        ta[t] = a_lo_base + ((a_off0 + (uint32_t)p.tap_off[t]) >> 4);
+        tacc_off[t] = (uint32_t)p.tap_acc[t];
+      }
+      const uint32_t fresh = p.tap_fresh ? (uint32_t)p.tap_fresh : 1u;
       const uint32_t s_btab_u32 = smem_u32(s_btab);
       if (p.b_resident) {
         for (int i = 0; i < k_iters; ++i)
@@ -571,11 +576,11 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 if (t < n_taps) {
-                  const uint32_t alo = sa4 + ta[t], blo = bl[t];
-                  umma_tf32(tacc, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k | t) ? 1u : 0u);
-                  umma_tf32(tacc, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
-                  umma_tf32(tacc, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
-                  umma_tf32(tacc, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
+                  const uint32_t alo = sa4 + ta[t], blo = bl[t], tt = tacc + tacc_off[t];
+                  umma_tf32(tt, mk64(alo, a_hi), mk64(blo, b_hi), idesc, (k == 0 && ((fresh >> t) & 1u)) ? 0u : 1u);
+                  umma_tf32(tt, mk64(alo + a_step, a_hi), mk64(blo + b_step, b_hi), idesc, 1u);
+                  umma_tf32(tt, mk64(alo + 2 * a_step, a_hi), mk64(blo + 2 * b_step, b_hi), idesc, 1u);
+                  umma_tf32(tt, mk64(alo + 3 * a_step, a_hi), mk64(blo + 3 * b_step, b_hi), idesc, 1u);
                 }
               }
             } else {
@@ -683,6 +688,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const int ext0[3] = {p.row_ext[0][0], p.row_ext[0][1], p.row_ext[0][2]};
     const bool r2_ok = r2 < p.row_box[2];
     const int epi = p.epilogue;
+    const int sub_panels = p.sub_panels;
     const float slope = p.slope;
     const bool bias_smem = p.nt * p.bn <= 512;
     const bool want_bits = p.bits_out != nullptr && epi == EPI_BIAS_LRELU;
@@ -690,6 +696,10 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     // the word index and the clipping test are then formed once per tile instead of once per panel
     const bool simple_panels = !SLAB && p.cols_per_map == 0 && p.d.period == 0 && p.d.panel[0] == 32 && p.d.panel[1] == 0 &&
                                p.d.panel[2] == 0 && p.d.panel[3] == 0 && p.d.panel[4] == 0;
+    // sub-tile mode with one channel panel per sub-tile: panel q = sub-tile q, the same channels `panel2` pixels further
+    const bool sub_regular = !SLAB && p.cols_per_map == 0 && sub_panels == 1;
+    const int sp1 = p.d.panel2[1], sp2 = p.d.panel2[2], sp3 = p.d.panel2[3];
+    const long sub_words = (sp1 * bs0 + sp2 * bs1 + sp3 * bs2) >> 5;
     const uint32_t s_bias_u32 = smem_u32(s_bias), my_staging_u32 = smem_u32(my_staging);
     int pc = 0, bi = 0;            // panels done so far, staging buffer of the current panel (pc % nbuf without the division)
     uint32_t bph = 0;              // (pc / nbuf) & 1
@@ -719,6 +729,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         return (base + cq[1] * bs0 + cq[2] * bs1 + cq[3] * bs2 + cq[0] + thread_bit_off) >> 5;
       };
       const long bw0 = (want_bits && simple_panels) ? bit_word(0) : -1;
+      // sub-tile mode: word of panel 0 without the clipping test; each panel tests its own shifted rows
+      const long sw0 = (bbase0 + cd[1] * bs0 + cd[2] * bs1 + cd[3] * bs2 + cd[0] + thread_bit_off) >> 5;
       unsigned mbits[8];
       if (bitmask) {  // issued before waiting for the accumulator: the loads overlap the tile's mainloop
 #pragma unroll
@@ -761,7 +773,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
           }
         }
-        const int col0 = n_tile * p.bn + q * 32;
+        // first channel of this panel (bias index / column guard): sub-tile mode repeats the channel panels per sub-tile
+        const int col0 = sub_panels > 0 ? (sub_panels == 1 ? 0 : (q % sub_panels) * 32) : n_tile * p.bn + q * 32;
         unsigned bits_w = 0u;
         long bits_wi = -1;
         if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) {
@@ -795,7 +808,14 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           unsigned w = (w4[0] | (w4[1] << 8)) | ((w4[2] << 16) | (w4[3] << 24));
           if (col0 + 32 > p.n_total) w &= (1u << (p.n_total - col0)) - 1u;   // partial last panel
           bits_w = w;
-          bits_wi = simple_panels ? (bw0 >= 0 ? bw0 + q : -1) : bit_word(q);
+          if (simple_panels) {
+            bits_wi = bw0 >= 0 ? bw0 + q : -1;
+          } else if (sub_regular) {
+            const bool ok = r2_ok && cd[1] + q * sp1 + r0 < ext0[0] && cd[2] + q * sp2 + r1 < ext0[1] && cd[3] + q * sp3 + r2 < ext0[2];
+            bits_wi = ok ? sw0 + q * sub_words : -1;
+          } else {
+            bits_wi = bit_word(q);
+          }
         }
         if (bitmask) {
           unsigned w = 0u;
