@@ -16,7 +16,9 @@ def test_contraction_exact_on_integers(case):
     assert P.run_case(case)
 
 
-@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (384, 100, 25632), (130, 3 * 32, 100)])
+# (2176 = 17 row tiles: CTA-pair mode with a phantom 18th tile; 4096 x 512: plain pair mode; the others: single-CTA paths)
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (384, 100, 25632), (130, 3 * 32, 100), (2176, 512, 544), (4096, 256, 512),
+                                   (2100, 160, 96)])
 def test_linear_tf32_rounding_level(M, N, K):
     from gail_carla_b200 import _abi as A
     g = torch.Generator().manual_seed(M + N + K)
@@ -30,6 +32,9 @@ def test_linear_tf32_rounding_level(M, N, K):
     ref = x[:, :K].double() @ w[:, :K].double().t() + b.double()
     rel = ((y[:, :N].cpu().double() - ref).norm() / ref.norm()).item()
     assert rel < 2e-3, rel
+    # every row individually (a mis-paired or clipped tile would leave whole rows wrong while the norm barely moves)
+    row_rel = (y[:, :N].cpu().double() - ref).norm(dim=1) / ref.norm(dim=1)
+    assert row_rel.max().item() < 1e-2, row_rel.argmax().item()
 
 
 def test_conv_stack_tf32_vs_fp64():
