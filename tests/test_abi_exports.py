@@ -49,3 +49,17 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", build_library()], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
         assert mnemonic in sass, mnemonic
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under gail_carla_b200/ may import, name or execute it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "gail_carla_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle\.", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8", errors="ignore").read()
+                assert not pat.search(text), f"{f} refers to the oracle"
