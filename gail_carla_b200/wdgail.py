@@ -135,6 +135,7 @@ class CriticEngine:
 
 
 class Discriminator(nn.Module):
+    N_STAGING = 3     # device staging sets of the expert-batch prefetch ring (prefetch depth N_STAGING - 1)
     def __init__(self, state_shape, metrics_space, action_space, hidden_dim, device, lr, eps, betas, max_grad_norm=None):
         super(Discriminator, self).__init__()
         if tuple(state_shape) != (3, 192, 192) or metrics_space.shape[0] != 4 or action_space.shape[0] != 2:
@@ -221,9 +222,10 @@ class Discriminator(nn.Module):
         """Yield ``(expert tensors on the device, idx, release)`` for every (expert batch, policy index batch) pair.
 
         The expert loader hands out host tensors (algo/wdgail.py:112,119; 1.8 GB per batch at B=4096).  They are uploaded
-        on a side stream into two preallocated device staging sets, so the copy of batch i+1 runs while batch i is being
-        processed; ``release()`` (called once the batch has been gathered into the workspace) lets the copy stream reuse
-        that staging set."""
+        on a side stream into a ring of three preallocated device staging sets, so the copies of batches i+1 and i+2 run
+        while batch i is being processed (two batches of slack: other host->device traffic - a rollout streaming in for
+        the next iteration - shares the DMA queue and would otherwise stall a minibatch every time it gets in front);
+        ``release()`` (called once the batch has been gathered into the workspace) lets the copy stream reuse that set."""
         dev = self._dev()
         if dev.type != "cuda":
             for batch, idx in pairs:
@@ -231,11 +233,12 @@ class Discriminator(nn.Module):
             return
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._stage_bufs = [None, None]
+            self._stage_bufs = [None] * self.N_STAGING
+        nsets = self.N_STAGING
         main = torch.cuda.current_stream(dev)
         trace = getattr(self, "_trace", None)      # diagnostics: list collecting (tag, start_event, end_event)
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [None, None]
+        ready = [torch.cuda.Event() for _ in range(nsets)]
+        consumed = [None] * nsets
 
         def stage(pair, k):
             batch, idx = pair
@@ -268,21 +271,32 @@ class Discriminator(nn.Module):
             return release
 
         it = iter(pairs)
-        try:
-            cur = stage(next(it), 0)
-        except StopIteration:
-            return
-        k = 0
-        while cur is not None:
+        pending = []                  # staged batches not yet handed out: [((tensors, idx), set index)]
+        state = {"next": 0, "done": False}
+
+        def stage_one():
             try:
-                nxt = stage(next(it), 1 - k)
+                pair = next(it)
             except StopIteration:
-                nxt = None
+                state["done"] = True
+                return
+            k = state["next"]
+            pending.append((stage(pair, k), k))
+            state["next"] = (k + 1) % nsets
+
+        while not state["done"] and len(pending) < nsets - 1:
+            stage_one()
+        while pending:
+            cur, k = pending.pop(0)
+            # the set handed out now is in use until release(); the other nsets-1 sets are staged ahead.  The set being
+            # refilled here belonged to the batch handed out (and released) in the previous iteration.
+            while not state["done"] and len(pending) < nsets - 1:
+                stage_one()
             main.wait_event(ready[k])
+            marker = consumed[k]
             yield cur[0], cur[1], releaser(k)
-            if consumed[k] is None:                          # caller forgot to release: be safe
+            if consumed[k] is marker:                        # caller forgot to release: be safe
                 releaser(k)()
-            cur, k = nxt, 1 - k
 
     # ---- algo/wdgail.py:100-147
     def update(self, expert_loader, rollouts):
