@@ -32,7 +32,7 @@ _SIGNATURES = {
     "gc_gae_returns": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
     "gc_adv_stats": [_P, _P, _P, _L, _P],
     "gc_adv_normalize": [_P, _P, _P, _P, _L, _P],
-    "gc_ppo_loss_fwd_bwd": [_P] * 11 + [_I, _F, _F, _I, _F, _F, _F, _I, _P],
+    "gc_ppo_loss_fwd_bwd": [_P] * 11 + [_I, _F, _F, _I, _F, _F, _F, _I, _I, _F, _P],
     "gc_policy_act": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _P],
     "gc_welford_merge": [_P, _P, _L, _P, _P],
     "gc_gather_obs_s2d": [_P, _P, _P, _I, _P],
@@ -43,8 +43,8 @@ _SIGNATURES = {
     "gc_metrics_features_bwd": [_P, _P, _P, _P, _L, _P, _I, _P],
     "gc_small_linear_fwd": [_P, _L, _P, _P, _P, _L, _I, _I, _I, _P],
     "gc_small_linear_bwd": [_P, _L, _P, _P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _F, _P],
-    "gc_disc_loss_seed": [_P, _P, _P, _I, _P],
-    "gc_grad_penalty": [_P, _P, _P, _I, _L, _F, _F, _F, _F, _P],
+    "gc_disc_loss_seed": [_P, _P, _P, _I, _F, _P],
+    "gc_grad_penalty": [_P, _P, _P, _I, _L, _F, _F, _F, _F, _F, _P],
     "gc_reward_epilogue": [_P, _P, _L, _P],
     "gc_colsum": [_P, _L, _L, _I, _P, _P],
     "gc_splitk_reduce": [_P, _I, _L, _I, _L, _P, _P, _L, _P, _L, _I, _F, _P],
@@ -52,8 +52,8 @@ _SIGNATURES = {
     "gc_unprep_conv_wgrad": [_P, _I, _P, _P, _I, _I, _I, _P],
     "gc_prep_fc1_weight": [_P, _P, _I, _I, _L, _P],
     "gc_unprep_fc1_wgrad": [_P, _I, _P, _I, _I, _L, _P],
-    "gc_grad_sumsq": [_P, _L, _P, _P],
-    "gc_clip_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _P],
+    "gc_grad_sumsq": [_P, _L, _F, _P, _P],
+    "gc_clip_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
     "gc_conv_fprop": [_G, _P, _P, _P, _P, _P, _P, _I, _F, _P],
     "gc_conv_dgrad": [_G, _P, _P, _P, _P, _P, _F, _P],
     "gc_conv_wgrad_splits": [_G],
@@ -62,7 +62,8 @@ _SIGNATURES = {
     "gc_linear_dgrad": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _F, _P],
     "gc_linear_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["gc_last_error_string", "gc_abi_version"])
+ABI_VERSION = 2            # == GC_ABI_VERSION of include/gail_carla_b200.h; bumped whenever a signature changes
+EXPORTS = sorted(list(_SIGNATURES) + ["gc_last_error_string", "gc_abi_version", "gc_build_digest"])
 
 
 def load_library() -> C.CDLL:
@@ -73,14 +74,28 @@ def load_library() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing - run `python -m gail_carla_b200.build` (no CPU fallback exists)")
     lib = C.CDLL(LIB_PATH)
+    lib.gc_abi_version.restype = C.c_int
+    lib.gc_abi_version.argtypes = []
+    if lib.gc_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has C-ABI version {lib.gc_abi_version()}, this package binds version {ABI_VERSION}: "
+                           "rebuild with `python -m gail_carla_b200.build`")
+    try:
+        lib.gc_build_digest.restype = C.c_char_p
+        lib.gc_build_digest.argtypes = []
+        built = lib.gc_build_digest().decode()
+    except AttributeError:
+        built = ""
+    from .build import source_digest
+    want = source_digest()
+    if want and built != want:      # a stale binary next to newer sources (e.g. after a pull): never run it
+        raise RuntimeError(f"{LIB_PATH} was built from different sources (digest {built[:12]} != {want[:12]}): "
+                           "rebuild with `python -m gail_carla_b200.build`")
     for name, args in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
     lib.gc_last_error_string.restype = C.c_char_p
     lib.gc_last_error_string.argtypes = []
-    lib.gc_abi_version.restype = C.c_int
-    lib.gc_abi_version.argtypes = []
     _lib = lib
     return lib
 
@@ -132,11 +147,14 @@ def adv_normalize(returns, value_preds, stats, out, n):
 
 
 def ppo_loss(head_out, actions, old_logp, value_old, returns, adv, adv_stats_, d_head, out_value, out_logp, loss_acc, B,
-             logstd, activation, clip, value_coef, action_weight, mode):
+             logstd, activation, clip, value_coef, action_weight, mode, clipped_value=True, norm=None):
+    """norm: number of samples the batch means run over (default B; a rank holding part of a global minibatch passes the
+    global row count)."""
     _contig(head_out, actions, old_logp, value_old, returns, adv, d_head, out_value, out_logp)
     call("gc_ppo_loss_fwd_bwd", _ptr(head_out), _ptr(actions), _ptr(old_logp), _ptr(value_old), _ptr(returns), _ptr(adv),
          _ptr(adv_stats_, torch.float64), _ptr(d_head), _ptr(out_value), _ptr(out_logp), _ptr(loss_acc, torch.float64), B,
-         float(logstd[0]), float(logstd[1]), int(bool(activation)), clip, value_coef, action_weight, mode, _stream())
+         float(logstd[0]), float(logstd[1]), int(bool(activation)), clip, value_coef, action_weight, mode,
+         int(bool(clipped_value)), 0.0 if norm is None else 1.0 / float(norm), _stream())
 
 
 def policy_act(head_out, noise, value, action, logp, B, logstd, activation):
@@ -189,13 +207,13 @@ def small_linear_bwd(x, ldx, w, dy, lddy, dx, lddx, dw, db, B, B_params, N, K, s
          slope, _stream())
 
 
-def disc_loss_seed(d, dd, acc, B):
-    call("gc_disc_loss_seed", _ptr(d), _ptr(dd), _ptr(acc, torch.float64), B, _stream())
+def disc_loss_seed(d, dd, acc, B, norm=None):
+    call("gc_disc_loss_seed", _ptr(d), _ptr(dd), _ptr(acc, torch.float64), B, 0.0 if norm is None else 1.0 / float(norm), _stream())
 
 
-def grad_penalty(g, u, acc, B, per_sample, lambda_, scales):
+def grad_penalty(g, u, acc, B, per_sample, lambda_, scales, norm=None):
     call("gc_grad_penalty", _ptr(g), _ptr(u), _ptr(acc, torch.float64), B, per_sample, lambda_, scales[0], scales[1], scales[2],
-         _stream())
+         0.0 if norm is None else 1.0 / float(norm), _stream())
 
 
 def reward_epilogue(d, reward, n):
@@ -230,13 +248,15 @@ def unprep_fc1_wgrad(part, splits, dw, out, tail, ld):
     call("gc_unprep_fc1_wgrad", _ptr(part), splits, _ptr(dw), out, tail, ld, _stream())
 
 
-def grad_sumsq(grad, n, sumsq):
-    call("gc_grad_sumsq", _ptr(grad), n, _ptr(sumsq, torch.float64), _stream())
+def grad_sumsq(grad, n, sumsq, grad_scale=1.0):
+    call("gc_grad_sumsq", _ptr(grad), n, float(grad_scale), _ptr(sumsq, torch.float64), _stream())
 
 
-def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2):
+def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2, grad_scale=1.0,
+              zero_grad=False, dev_hyper=None):
     call("gc_clip_adam", _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, _ptr(sumsq, torch.float64),
-         -1.0 if max_norm is None else float(max_norm), lr, beta1, beta2, eps, bc1, bc2, _stream())
+         -1.0 if max_norm is None else float(max_norm), lr, beta1, beta2, eps, bc1, bc2, float(grad_scale), int(bool(zero_grad)),
+         _ptr(dev_hyper), _stream())
 
 
 # ------------------------------------------------------------------ tcgen05 contractions

@@ -34,10 +34,31 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def source_digest() -> str:
+    """Digest of the sources next to this file, or "" when they are not there (a binary-only deployment)."""
+    try:
+        return _digest()
+    except OSError:
+        return ""
+
+
+def built_digest() -> str:
+    """The digest embedded in the built library (gc_build_digest), "" if there is no library or it predates the export."""
+    if not os.path.exists(LIB_PATH):
+        return ""
+    import ctypes
+    try:
+        fn = ctypes.CDLL(LIB_PATH).gc_build_digest
+    except (OSError, AttributeError):
+        return ""
+    fn.restype = ctypes.c_char_p
+    return fn().decode()
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    stamp = LIB_PATH + ".sha256"
+    # the digest lives INSIDE the binary (no side-car stamp file that version control could update behind a stale .so)
     dig = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
+    if not force and built_digest() == dig:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
@@ -46,7 +67,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, f'-DGC_BUILD_DIGEST="{dig}"', "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -57,8 +78,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
     subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"])
-    with open(stamp, "w") as fh:
-        fh.write(dig)
     return LIB_PATH
 
 

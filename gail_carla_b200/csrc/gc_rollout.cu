@@ -214,7 +214,7 @@ __device__ __forceinline__ HeadTail head_tail(const float4 h, const float a0, co
 // one sample of the fused head tail + PPO / BC loss: returns d loss / d head row, adds this sample's loss terms to part[]
 struct PpoConsts {
   float ls0, ls1, clip, vcoef, w_act, inv_B, mean, inv;
-  int activation, mode;
+  int activation, mode, clipped_value;
 };
 __device__ __forceinline__ float4 ppo_sample(const PpoConsts& c, const float4 h, const float2 a, const float olp, const float vo,
                                              const float R, const float adv_or_nan, const bool has_adv, double (&part)[3],
@@ -236,17 +236,22 @@ __device__ __forceinline__ float4 ppo_sample(const PpoConsts& c, const float4 h,
     else dr = A * (0.5f + 0.5f * in_rng);
     dlogp = -c.w_act * c.inv_B * dr * ratio;
     part[1] += (double)(-fminf(sa, sb));
-    // clipped value loss
-    const float dvv = t.v - vo;
-    const float vc = vo + fminf(fmaxf(dvv, -c.clip), c.clip);
-    const float l1 = (t.v - R) * (t.v - R), l2 = (vc - R) * (vc - R);
-    const float vin = (dvv >= -c.clip && dvv <= c.clip) ? 1.f : 0.f;
-    float g;  // d max(l1,l2) / d v
-    if (l1 > l2) g = 2.f * (t.v - R);
-    else if (l1 < l2) g = 2.f * (vc - R) * vin;
-    else g = (t.v - R) + (vc - R) * vin;
-    dv = c.vcoef * 0.5f * c.inv_B * g;
-    part[0] += (double)(0.5f * fmaxf(l1, l2));
+    const float l1 = (t.v - R) * (t.v - R);
+    if (c.clipped_value) {  // clipped value loss (algo/ppo.py:104-111)
+      const float dvv = t.v - vo;
+      const float vc = vo + fminf(fmaxf(dvv, -c.clip), c.clip);
+      const float l2 = (vc - R) * (vc - R);
+      const float vin = (dvv >= -c.clip && dvv <= c.clip) ? 1.f : 0.f;
+      float g;  // d max(l1,l2) / d v
+      if (l1 > l2) g = 2.f * (t.v - R);
+      else if (l1 < l2) g = 2.f * (vc - R) * vin;
+      else g = (t.v - R) + (vc - R) * vin;
+      dv = c.vcoef * 0.5f * c.inv_B * g;
+      part[0] += (double)(0.5f * fmaxf(l1, l2));
+    } else {  // 0.5 * (return - value)^2 (algo/ppo.py:112-113)
+      dv = c.vcoef * c.inv_B * (t.v - R);
+      part[0] += (double)(0.5f * l1);
+    }
   } else if (c.mode == 1) {
     dlogp = -c.w_act * c.inv_B;
     part[2] += (double)(-t.logp);
@@ -268,9 +273,10 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const float4* __restrict_
                                                        const double* __restrict__ stats, float4* __restrict__ d_head,
                                                        float* __restrict__ out_value, float* __restrict__ out_logp,
                                                        double* __restrict__ acc, int B, float ls0, float ls1, int activation,
-                                                       float clip, float vcoef, float w_act, float inv_B, int mode) {
+                                                       float clip, float vcoef, float w_act, float inv_B, int mode,
+                                                       int clipped_value) {
   __shared__ double red[32 * 3];
-  PpoConsts c{ls0, ls1, clip, vcoef, w_act, inv_B, 0.f, 1.f, activation, mode};
+  PpoConsts c{ls0, ls1, clip, vcoef, w_act, inv_B, 0.f, 1.f, activation, mode, clipped_value};
   if (mode == 0 && adv_in == nullptr) adv_moments(stats, c.mean, c.inv);
   double part[3] = {0.0, 0.0, 0.0};
   const bool has_adv = adv_in != nullptr;
@@ -374,6 +380,11 @@ const char* gc_last_error_string(void) { return gc::last_error().c_str(); }
 
 int gc_abi_version(void) { return GC_ABI_VERSION; }
 
+#ifndef GC_BUILD_DIGEST
+#define GC_BUILD_DIGEST "unknown"
+#endif
+const char* gc_build_digest(void) { return GC_BUILD_DIGEST; }
+
 int gc_gae_returns(const float* gail_rewards, const float* value_preds, const float* masks, float* returns, float* adv_raw,
                    double* stats, int T, int N, float gamma, float gae_lambda, void* stream) {
   GC_REQUIRE(T > 0 && N > 0, "gc_gae_returns: T=%d N=%d must be positive", T, N);
@@ -434,7 +445,8 @@ int gc_adv_normalize(const float* returns, const float* value_preds, const doubl
 int gc_ppo_loss_fwd_bwd(const float* head_out, const float* actions, const float* old_logp, const float* value_old,
                         const float* returns, const float* adv, const double* adv_stats, float* d_head_out,
                         float* out_value, float* out_logp, double* loss_acc, int B, float logstd0, float logstd1,
-                        int activation, float clip, float value_coef, float action_weight, int mode, void* stream) {
+                        int activation, float clip, float value_coef, float action_weight, int mode, int clipped_value,
+                        float inv_norm, void* stream) {
   GC_REQUIRE(B > 0, "gc_ppo_loss_fwd_bwd: B=%d", B);
   GC_REQUIRE(mode >= 0 && mode <= 2, "gc_ppo_loss_fwd_bwd: mode %d not in {0,1,2}", mode);
   GC_REQUIRE(head_out && actions, "gc_ppo_loss_fwd_bwd: null head/actions");
@@ -449,7 +461,8 @@ int gc_ppo_loss_fwd_bwd(const float* head_out, const float* actions, const float
   const int grid = std::min((B / 4 + 255) / 256 + 1, 8 * gc::kNumSMs);
   ppo_loss_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const float4*)head_out, (const float2*)actions, old_logp, value_old, returns, adv, adv_stats, (float4*)d_head_out,
-      out_value, out_logp, loss_acc, B, logstd0, logstd1, activation, clip, value_coef, action_weight, 1.0f / (float)B, mode);
+      out_value, out_logp, loss_acc, B, logstd0, logstd1, activation, clip, value_coef, action_weight,
+      inv_norm > 0.f ? inv_norm : 1.0f / (float)B, mode, clipped_value);
   return gc::launch_status("ppo_loss_kernel");
 }
 

@@ -185,10 +185,10 @@ __global__ void small_linear_dw_kernel(const float* __restrict__ x, long ldx, co
     for (int j = 0; j < N; ++j) atomicAdd(db + j, accb[j]);
 }
 
-__global__ void disc_loss_seed_kernel(const float* __restrict__ d, float* __restrict__ dd, double* __restrict__ acc, int B) {
+__global__ void disc_loss_seed_kernel(const float* __restrict__ d, float* __restrict__ dd, double* __restrict__ acc, int B,
+                                      float invB) {
   __shared__ double red[32 * 4];
   double part[4] = {0.0, 0.0, 0.0, 0.0};
-  const float invB = 1.f / (float)B;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * B; i += gridDim.x * blockDim.x) {
     const float v = d[i];
     if (i < 2 * B) {
@@ -207,8 +207,8 @@ __global__ void disc_loss_seed_kernel(const float* __restrict__ d, float* __rest
 
 // one CTA per sample: ||g_raw|| then u = lambda*2*(||g||-1)/(B*||g||) * s_c^2 * g
 __global__ void __launch_bounds__(512) grad_penalty_kernel(const float4* __restrict__ g, float4* __restrict__ u,
-                                                           double* __restrict__ acc, int B, long per4, float lambda_, float s0,
-                                                           float s1, float s2) {
+                                                           double* __restrict__ acc, float inv_norm, long per4, float lambda_,
+                                                           float s0, float s1, float s2) {
   __shared__ double red[32];
   __shared__ float s_coef;
   const int b = blockIdx.x;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(512) grad_penalty_kernel(const float4* __restr
     const float nrm = (float)sqrt(part[0]);
     const float diff = nrm - 1.f;
     atomicAdd(acc, (double)diff * diff);
-    s_coef = nrm > 0.f ? lambda_ * 2.f * diff / ((float)B * nrm) : 0.f;
+    s_coef = nrm > 0.f ? lambda_ * 2.f * diff * inv_norm / nrm : 0.f;
   }
   __syncthreads();
   const float k0 = s_coef * s0 * s0, k1 = s_coef * s1 * s1, k2 = s_coef * s2 * s2;
@@ -355,7 +355,7 @@ __global__ void unprep_fc1_kernel(const float* __restrict__ part, int splits, fl
 }
 
 // ---- clip_grad_norm_ + Adam ---------------------------------------------------------------------------------
-__global__ void grad_sumsq_kernel(const float* __restrict__ g, long n, double* __restrict__ out) {
+__global__ void grad_sumsq_kernel(const float* __restrict__ g, long n, float scale, double* __restrict__ out) {
   __shared__ double red[32];
   float s = 0.f;
   double tot = 0.0;
@@ -368,7 +368,7 @@ __global__ void grad_sumsq_kernel(const float* __restrict__ g, long n, double* _
     if (++cnt == 64) { tot += s; s = 0.f; cnt = 0; }
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = g[(n4 << 2) + threadIdx.x]; s += v * v; }
-  double part[1] = {tot + s};
+  double part[1] = {(tot + s) * ((double)scale * (double)scale)};
   gc::block_sum<1>(part, red);
   if (threadIdx.x == 0) atomicAdd(out, part[0]);
 }
@@ -384,12 +384,19 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
 
 __global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long n,
                                  const double* __restrict__ sumsq, float max_norm, float lr, float b1, float b2, float eps,
-                                 float bc1, float bc2) {
+                                 float bc1, float bc2, float grad_scale, int zero_grad, const float* __restrict__ dev_hyper) {
+  if (dev_hyper) {  // {lr, 1-beta1^t, 1-beta2^t} refreshed by the host between replays of a captured graph
+    lr = dev_hyper[0];
+    bc1 = dev_hyper[1];
+    bc2 = dev_hyper[2];
+  }
   float coef = 1.f;
   if (max_norm >= 0.f) {
     const float total = (float)sqrt(*sumsq);
     coef = fminf(max_norm / (total + 1e-6f), 1.f);
   }
+  coef *= grad_scale;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   const float lr_c = lr / bc1, isb = 1.f / sqrtf(bc2);
   const long n4 = n >> 2;
   float4 *p4 = reinterpret_cast<float4*>(p), *m4 = reinterpret_cast<float4*>(m), *v4 = reinterpret_cast<float4*>(v);
@@ -401,10 +408,12 @@ __global__ void clip_adam_kernel(float* __restrict__ p, float* __restrict__ g, f
     adam1(P.z, G.z, M.z, V.z, coef, lr_c, b1, b2, eps, isb);
     adam1(P.w, G.w, M.w, V.w, coef, lr_c, b1, b2, eps, isb);
     p4[i] = P; m4[i] = M; v4[i] = V;
+    if (zero_grad) g4[i] = z4;
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const long i = (n4 << 2) + threadIdx.x;
     adam1(p[i], g[i], m[i], v[i], coef, lr_c, b1, b2, eps, isb);
+    if (zero_grad) g[i] = 0.f;
   }
 }
 
@@ -486,16 +495,18 @@ int gc_small_linear_bwd(const float* x, long ldx, const float* w, const float* d
   return 0;
 }
 
-int gc_disc_loss_seed(const float* d, float* dd, double* acc, int B, void* stream) {
+int gc_disc_loss_seed(const float* d, float* dd, double* acc, int B, float inv_norm, void* stream) {
   GC_REQUIRE(d && dd && acc && B > 0, "gc_disc_loss_seed: bad arguments");
-  disc_loss_seed_kernel<<<grid_for(3L * B, 256, 2), 256, 0, (cudaStream_t)stream>>>(d, dd, acc, B);
+  disc_loss_seed_kernel<<<grid_for(3L * B, 256, 2), 256, 0, (cudaStream_t)stream>>>(d, dd, acc, B,
+                                                                                    inv_norm > 0.f ? inv_norm : 1.f / (float)B);
   return gc::launch_status("disc_loss_seed_kernel");
 }
 
 int gc_grad_penalty(const float* g, float* u, double* acc, int B, long per_sample, float lambda_, float s0, float s1, float s2,
-                    void* stream) {
+                    float inv_norm, void* stream) {
   GC_REQUIRE(g && u && acc && B > 0 && per_sample % 4 == 0, "gc_grad_penalty: bad arguments");
-  grad_penalty_kernel<<<B, 512, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)u, acc, B, per_sample / 4, lambda_, s0, s1, s2);
+  grad_penalty_kernel<<<B, 512, 0, (cudaStream_t)stream>>>((const float4*)g, (float4*)u, acc, inv_norm > 0.f ? inv_norm : 1.f / (float)B,
+                                                           per_sample / 4, lambda_, s0, s1, s2);
   return gc::launch_status("grad_penalty_kernel");
 }
 
@@ -567,21 +578,23 @@ int gc_unprep_fc1_wgrad(const float* part, int splits, float* dw, int out, int t
   return gc::launch_status("unprep_fc1_kernel");
 }
 
-int gc_grad_sumsq(const float* grad, long n, double* sumsq, void* stream) {
+int gc_grad_sumsq(const float* grad, long n, float grad_scale, double* sumsq, void* stream) {
   GC_REQUIRE(grad && sumsq && n > 0, "gc_grad_sumsq: bad arguments");
   GC_REQUIRE(((uintptr_t)grad & 15) == 0, "gc_grad_sumsq: grad must be 16-byte aligned");
-  grad_sumsq_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(grad, n, sumsq);
+  grad_sumsq_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(grad, n, grad_scale, sumsq);
   return gc::launch_status("grad_sumsq_kernel");
 }
 
 int gc_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long n, const double* sumsq, float max_norm,
-                 float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2, void* stream) {
+                 float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2, float grad_scale,
+                 int zero_grad, const float* dev_hyper, void* stream) {
   GC_REQUIRE(param && grad && exp_avg && exp_avg_sq && n > 0, "gc_clip_adam: bad arguments");
   GC_REQUIRE(max_norm < 0.f || sumsq, "gc_clip_adam: clipping needs sumsq");
   GC_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0,
              "gc_clip_adam: buffers must be 16-byte aligned");
   clip_adam_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm,
-                                                                               lr, beta1, beta2, eps, bias_corr1, bias_corr2);
+                                                                               lr, beta1, beta2, eps, bias_corr1, bias_corr2, grad_scale, zero_grad,
+                                                                               dev_hyper);
   return gc::launch_status("clip_adam_kernel");
 }
 

@@ -75,6 +75,27 @@ class FlatParams:
             p.data = flat[o:o + p.numel()].view(p.shape)
             p.grad = grad[o:o + p.numel()].view(p.shape)
         self.flat, self.grad = flat, grad
+        self.grad_clean = True     # the gradient buffer is all zeros (fresh, or zeroed by the fused clip+Adam kernel)
+
+    def begin_backward(self) -> None:
+        """optimizer.zero_grad() (algo/ppo.py:115, algo/wdgail.py:140): a no-op when the last optimiser step already
+        left zeros behind (gc_clip_adam zero_grad=1), else one memset."""
+        if not self.grad_clean:
+            self.grad.zero_()
+        self.grad_clean = False
+
+    def span(self, first: str, last: str = None):
+        """[lo, hi) element range of the flat buffers covering parameters `first`..`last` (inclusive, declaration order)."""
+        names = self.names
+        i0 = names.index(first)
+        i1 = names.index(last) if last is not None else len(names) - 1
+        hi = self.offsets[names[i1 + 1]] if i1 + 1 < len(names) else self.numel
+        return self.offsets[names[i0]], hi
+
+    def version(self) -> int:
+        """Sum of the parameters' autograd version counters: changes whenever torch code (an external optimiser,
+        load_state_dict, a manual ``p.data.copy_``) writes a parameter in place, so stale operand copies are rebuilt."""
+        return sum(p._version for p in self.module.parameters())
 
     def ok(self) -> bool:
         """True while every parameter is still a view of the flat buffer (``.to()`` / ``.cpu()`` break that)."""
@@ -114,6 +135,11 @@ class Workspace:
         self.part: Dict[str, torch.Tensor] = {}
         self.small: Dict[str, torch.Tensor] = {}
 
+    def release(self) -> None:
+        """Drop every buffer (engines may still hold a reference to a workspace that has been replaced by a larger one)."""
+        self.X0 = self.F = self.dA = None
+        self.A, self.mbits, self.part, self.small, self.rows = [], [], {}, {}, 0
+
     def grads(self):
         if self.dA is None:
             z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
@@ -150,6 +176,7 @@ def shared_workspace(device, rows: int, with_input_grad: bool) -> Workspace:
     if ws is None or ws.rows < rows:
         if ws is not None:
             _SHARED.pop(key)
+            ws.release()           # PolicyEngine.ws / CriticEngine.ws may still point at it: free its buffers now
             del ws
             if torch.cuda.is_available():
                 torch.cuda.empty_cache()
@@ -276,8 +303,3 @@ def linear_wgrad(ws: Workspace, key: str, dy, lddy, x, ldx, dw, lddw, M, N, K) -
     A.splitk_reduce(part, splits, M, N, lddw, None, None, 0, dw, lddw, EPI_STORE, SLOPE)
 
 
-class MLPSpec:
-    """One hidden nn.Linear + LeakyReLU layer handled by the tensor-core GEMM (weight read in place)."""
-
-    def __init__(self, name: str, fin: int, fout: int):
-        self.name, self.fin, self.fout = name, fin, fout

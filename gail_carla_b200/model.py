@@ -64,6 +64,9 @@ class PolicyEngine:
         dev = self.flat.flat.device
         if dev.type != "cuda" and not getattr(A, "EMULATED", False):
             raise RuntimeError("gail_carla_b200.Policy runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        ver = self.flat.version()
+        if ver != getattr(self, "_version", None):     # torch code wrote a parameter in place since the last preparation
+            self.dirty, self._version = True, ver
         if moved or self.dirty or self.w1 is None or self.w1.device != dev:
             if self.w1 is None or self.w1.device != dev:
                 self.w1 = torch.zeros(512, LDF, dtype=torch.float32, device=dev)
@@ -105,10 +108,12 @@ class PolicyEngine:
         return out
 
     # ---- backward ----------------------------------------------------------------------------------------
-    def backward(self, B: int, d_head: torch.Tensor) -> None:
-        """d loss / d head_out [B,4] -> gradients of every parameter (written into the flat grad buffer)."""
+    def backward(self, B: int, d_head: torch.Tensor, reducer=None) -> None:
+        """d loss / d head_out [B,4] -> gradients of every parameter (written into the flat grad buffer).
+        `reducer` (optim.GradReducer): told when a slice of the gradient buffer is final, so the multi-GPU all-reduce of
+        the fully connected layers (90 % of the bytes) overlaps the convolution gradients."""
         ws, P, G = self.ws, self.flat.p, self.flat.g
-        self.flat.grad.zero_()
+        self.flat.begin_backward()
         dA = ws.grads()
         hs = [ws.buf("h1", ws.rows, 512)] + [ws.buf(f"h{i + 2}", ws.rows, f[2]) for i, f in enumerate(HIDDEN)]
         # head.2 (256 -> 3): SIMT; dx masked by LeakyReLU'(h4)
@@ -135,6 +140,8 @@ class PolicyEngine:
                        mask_bits=ws.mbits[4])
         A.linear_dgrad(d, 512, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, B, 32, 512)
         A.metrics_features_bwd(ws.buf("metrics", ws.rows, 4), ws.dFt, 32, G("base.metrics_processor.road_option_embedding.weight"), B)
+        if reducer is not None:     # embedding + every Linear are final; the convolutions come first in the flat order
+            reducer.ready(self.flat, *self.flat.span("base.metrics_processor.road_option_embedding.weight"))
         self.conv.backward_data(ws, B)
         self.conv.backward_params(ws, B, B)
 
@@ -181,16 +188,18 @@ class Policy(nn.Module):
         self.mark_params_changed()
         return r
 
-    def _run(self, obs, metrics) -> tuple:
+    def _run(self, obs, metrics, training: bool = False) -> tuple:
         eng = self.engine
         eng.sync_params()
         dev = eng.flat.flat.device
-        obs = obs.to(dev, torch.float32).contiguous()
+        if obs.dtype != torch.uint8:
+            obs = obs.to(dev, torch.float32)
+        obs = obs.to(dev).contiguous()
         metrics = metrics.to(dev, torch.float32).contiguous()
         B = obs.shape[0]
         eng.workspace(B)
         eng.load_inputs(obs, metrics, None, B)
-        return eng, eng.forward(B), B
+        return eng, eng.forward(B, training=training), B
 
     def act(self, obs, metrics, deterministic=False):
         """tools/model.py:25-36 -> (value [B,1], action [B,2], action_log_probs [B,1])."""
@@ -211,14 +220,76 @@ class Policy(nn.Module):
             return head[:B, 0:1].clone()
 
     def evaluate_actions(self, obs, metrics, action):
-        """tools/model.py:45-53 -> (value, log-probs, entropy, steer log-std, throttle log-std); forward only.
-        (PPO.update uses the fused forward+backward path instead of autograd.)"""
+        """tools/model.py:45-53 -> (value, log-probs, entropy, steer log-std, throttle log-std).
+
+        ``value`` and ``log-probs`` are differentiable w.r.t. the parameters (the reference's learn_bc.py:37-45 calls
+        ``.backward()`` on a loss built from them): under ``torch.enable_grad()`` they carry a grad_fn whose backward
+        runs the hand-derived trunk backward of the engine and accumulates into ``p.grad``.  The activations live in
+        the shared workspace, so ``backward()`` must run before the next forward of this policy (it raises
+        otherwise).  PPO.update does not come through here - it uses the fused loss forward+backward kernel."""
+        ls = self.base.logstd
+        entropy = (0.5 + 0.5 * torch.log(torch.tensor(2 * torch.pi)) + ls).sum()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            value, logp = _EvaluateActions.apply(self, obs, metrics, action, *self.parameters())
+        else:
+            with torch.no_grad():
+                value, logp = _evaluate_forward(self, obs, metrics, action, training=False)
+        return value, logp, entropy.to(value.device), ls[0].clone(), ls[1].clone()
+
+
+def _evaluate_forward(policy: Policy, obs, metrics, action, training: bool):
+    eng, head, B = policy._run(obs, metrics, training=training)
+    dev = head.device
+    value = torch.empty(B, 1, device=dev); logp = torch.empty(B, 1, device=dev)
+    A.ppo_loss(head, action.to(dev, torch.float32).contiguous(), None, None, None, None, None, None, value, logp, None, B,
+               policy.base.logstd.tolist(), policy.base.activation, 0.0, 0.0, 0.0, 2)
+    return value, logp
+
+
+class _EvaluateActions(torch.autograd.Function):
+    """Autograd bridge of ``Policy.evaluate_actions``: forward = engine forward (training mode: LeakyReLU' bit masks are
+    kept), backward = fused head-tail derivative (gc_ppo_loss_fwd_bwd, BC mode with unit weight gives d logp / d head)
+    + the engine's hand-derived trunk backward.  The parameters are passed as inputs only so that autograd routes their
+    gradients; the gradients are accumulated like autograd would (``p.grad += ...``)."""
+
+    @staticmethod
+    def forward(ctx, policy, obs, metrics, action, *params):
+        value, logp = _evaluate_forward(policy, obs, metrics, action, training=True)
+        eng = policy.engine
+        eng.forward_serial = getattr(eng, "forward_serial", 0) + 1
+        ctx.policy, ctx.serial, ctx.B = policy, eng.forward_serial, value.shape[0]
+        ctx.action = action.to(value.device, torch.float32).contiguous()
+        return value, logp
+
+    @staticmethod
+    def backward(ctx, g_value, g_logp):
+        policy, B = ctx.policy, ctx.B
+        eng = policy.engine
+        if eng.forward_serial != ctx.serial or eng.ws is None or eng.ws.rows < B:
+            raise RuntimeError("evaluate_actions: backward() must run before the next forward pass of this Policy "
+                               "(activations live in the shared workspace)")
+        ws = eng.ws
         with torch.no_grad():
-            eng, head, B = self._run(obs, metrics)
-            dev = head.device
-            value = torch.empty(B, 1, device=dev); logp = torch.empty(B, 1, device=dev)
-            A.ppo_loss(head, action.to(dev, torch.float32).contiguous(), None, None, None, None, None, None, value, logp, None, B,
-                       self.base.logstd.tolist(), self.base.activation, 0.0, 0.0, 0.0, 2)
-            ls = self.base.logstd
-            entropy = (0.5 + 0.5 * torch.log(torch.tensor(2 * torch.pi)) + ls).sum()
-            return value, logp, entropy.to(dev), ls[0].clone(), ls[1].clone()
+            head = ws.buf("head", ws.rows, 4)
+            d_head = ws.buf("dhead", ws.rows, 4)
+            # BC mode with weight -1 and norm 1: d_head[b] = d logp_b / d head_b (column 0 = 0)
+            A.ppo_loss(head, ctx.action, None, None, None, None, None, d_head, None, None, None, B,
+                       policy.base.logstd.tolist(), policy.base.activation, 0.0, 0.0, -1.0, 1, norm=1)
+            gl = torch.zeros(B, 1, device=head.device) if g_logp is None else g_logp.reshape(B, 1).to(head.device, torch.float32)
+            d_head[:B].mul_(gl)
+            if g_value is not None:
+                d_head[:B, 0:1].copy_(g_value.reshape(B, 1))
+            flat = eng.flat
+            keep = None if flat.grad_clean else flat.grad.clone()
+            eng.backward(B, d_head)
+            grads = tuple(p.grad.clone() if p.requires_grad else None for p in policy.parameters())
+            if keep is None:
+                flat.grad.zero_(); flat.grad_clean = True
+            else:
+                flat.grad.copy_(keep)
+        for p, g in zip(policy.parameters(), grads):      # accumulate like autograd (p.grad is a view of the flat buffer)
+            if g is not None:
+                p.grad.add_(g)
+        flat.grad_clean = False
+        eng.forward_serial += 1
+        return (None, None, None, None) + tuple(None for _ in grads)

@@ -3,16 +3,69 @@ flat parameter / gradient buffers, with the NCCL gradient all-reduce in between 
 
 The object is a real ``torch.optim.Optimizer`` so the reference's drivers can keep mutating
 ``optimizer.param_groups[i]['lr']`` (tools/utli.py:121-125, tools/learn.py:102-106).
+
+Multi-GPU: every rank holds the gradient of its rows of the global minibatch.  The engines hand
+finished slices of the flat gradient buffer to :class:`GradReducer` while the backward pass is still running (the fully
+connected layers - 90 % of the bytes - are final before the convolution gradients start), so the NCCL all-reduce runs
+on a side stream under the remaining dgrad / wgrad launches; ``step()`` reduces whatever is left, joins the streams and
+runs norm + clip + Adam.  The 1/world factor of the gradient mean and ``optimizer.zero_grad()`` are folded into those
+two kernels (no extra passes over the gradient).
 """
 from __future__ import annotations
 
-from typing import Optional
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
 from . import _abi as A
 from .engine import FlatParams
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class GradReducer:
+    """Sum-all-reduces slices of a flat gradient buffer on a side stream, in the order they become final."""
+
+    def __init__(self):
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.done: List[Tuple[int, int]] = []
+
+    def _side(self, dev) -> Optional[torch.cuda.Stream]:
+        if dev.type != "cuda":
+            return None
+        if self.stream is None or self.stream.device != dev:
+            self.stream = torch.cuda.Stream(device=dev)
+        return self.stream
+
+    def ready(self, flat: FlatParams, lo: int, hi: int) -> None:
+        """Elements [lo, hi) of ``flat.grad`` are final on the current stream: start reducing them."""
+        if world_size() == 1 or hi <= lo:
+            return
+        side = self._side(flat.grad.device)
+        if side is None:                       # gloo / CPU tests: reduce in line
+            dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
+        else:
+            side.wait_stream(torch.cuda.current_stream(flat.grad.device))
+            with torch.cuda.stream(side):
+                dist.all_reduce(flat.grad[lo:hi], op=dist.ReduceOp.SUM)
+        self.done.append((lo, hi))
+
+    def finish(self, flat: FlatParams) -> None:
+        """Reduce every element not handed over through ``ready`` and make the current stream wait for all of it."""
+        if world_size() == 1:
+            self.done = []
+            return
+        pos = 0
+        for lo, hi in sorted(self.done) + [(flat.numel, flat.numel)]:
+            if lo > pos:
+                self.ready(flat, pos, lo)
+            pos = max(pos, hi)
+        self.done = []
+        if self.stream is not None and flat.grad.device.type == "cuda":
+            torch.cuda.current_stream(flat.grad.device).wait_stream(self.stream)
 
 
 class FusedClipAdam(torch.optim.Optimizer):
@@ -23,6 +76,11 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.t = 0
         self._m = self._v = self._sumsq = None
         self._owner = None
+        self.reducer = GradReducer()
+        # gradient scale applied inside the norm / Adam kernels: None = 1/world (mean of per-rank mean gradients, equal
+        # shards); exact mode sets 1.0 (per-rank gradients are already weighted by 1/B_global and only need summing)
+        self.grad_scale: Optional[float] = None
+        self._hyper_host = self._hyper_dev = None
 
     def _buffers(self, flat: FlatParams):
         if self._m is None or self._owner is not flat.flat or self._m.device != flat.flat.device:
@@ -33,25 +91,46 @@ class FusedClipAdam(torch.optim.Optimizer):
                 self._m.copy_(old_m); self._v.copy_(old_v)
             self._sumsq = torch.zeros(1, dtype=torch.float64, device=flat.flat.device)
             self._owner = flat.flat
+            self._hyper_host = self._hyper_dev = None
+
+    # ---- step-dependent scalars kept on the device so a captured graph of the step can be replayed -----------
+    def device_hyper(self, flat: FlatParams) -> torch.Tensor:
+        if self._hyper_dev is None:
+            dev = flat.flat.device
+            self._hyper_host = torch.zeros(3, pin_memory=dev.type == "cuda")
+            self._hyper_dev = torch.zeros(3, device=dev)
+        return self._hyper_dev
+
+    def advance(self, flat: FlatParams) -> None:
+        """t += 1 and upload {lr, 1-beta1^t, 1-beta2^t} for the next (graph-replayed) step."""
+        self.t += 1
+        g = self.param_groups[0]
+        b1, b2 = g["betas"]
+        hd = self.device_hyper(flat)
+        self._hyper_host[0] = float(g["lr"]); self._hyper_host[1] = 1.0 - b1 ** self.t; self._hyper_host[2] = 1.0 - b2 ** self.t
+        hd.copy_(self._hyper_host, non_blocking=True)
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, *, from_device_hyper: bool = False):
         flat: FlatParams = self._flat_getter()
         self._buffers(flat)
         g = self.param_groups[0]
         n = flat.numel
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            # replicas hold equal-size minibatch shards: mean of the per-rank mean-gradients == global-batch gradient
-            dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
-            flat.grad.mul_(1.0 / dist.get_world_size())
-        self.t += 1
+        world = world_size()
+        self.reducer.finish(flat)
+        scale = self.grad_scale if self.grad_scale is not None else 1.0 / world
+        if not from_device_hyper:
+            self.t += 1
         b1, b2 = g["betas"]
         if self.max_grad_norm is not None:
             self._sumsq.zero_()
-            A.grad_sumsq(flat.grad, n, self._sumsq)
+            A.grad_sumsq(flat.grad, n, self._sumsq, scale)
         A.clip_adam(flat.flat, flat.grad, self._m, self._v, n, self._sumsq, self.max_grad_norm, float(g["lr"]), float(b1),
-                    float(b2), float(g["eps"]), 1.0 - b1 ** self.t, 1.0 - b2 ** self.t)
+                    float(b2), float(g["eps"]), 1.0 - b1 ** max(self.t, 1), 1.0 - b2 ** max(self.t, 1), scale, True,
+                    self.device_hyper(flat) if from_device_hyper else None)
+        flat.grad_clean = True
 
     def zero_grad(self, set_to_none: bool = False):   # gradients live in the flat buffer; never detach them
         flat: FlatParams = self._flat_getter()
         flat.grad.zero_()
+        flat.grad_clean = True

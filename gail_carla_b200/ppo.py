@@ -15,14 +15,12 @@ import torch.distributed as dist
 
 from . import _abi as A
 from .expert import expert_rows
-from .optim import FusedClipAdam
+from .optim import FusedClipAdam, world_size
 
 
 class PPO():
     def __init__(self, actor_critic, clip_param, ppo_epoch, mini_batch_size, value_loss_coef, device, lr=None, eps=None,
                  betas=None, max_grad_norm=None, use_clipped_value_loss=True, gamma=None, decay=None, act_space=None):
-        if not use_clipped_value_loss:
-            raise NotImplementedError("the reference always trains with use_clipped_value_loss=True (wdail_carla.py:211-224)")
         self.actor_critic = actor_critic
         self.clip_param = clip_param
         self.ppo_epoch = ppo_epoch
@@ -35,6 +33,12 @@ class PPO():
         self.max_grad_norm = max_grad_norm
         self.use_clipped_value_loss = use_clipped_value_loss
         self.optimizer = FusedClipAdam(lambda: actor_critic.engine.flat, actor_critic.parameters(), lr, eps, betas, max_grad_norm)
+        # Multi-GPU (torch.distributed initialised, envs sharded across ranks).  False: every rank
+        # permutes its own env shard and `mini_batch_size` is the per-rank share of the global minibatch (equal shards,
+        # mean of means).  True ("exact mode", needs rollouts.set_shard): one global permutation, global minibatches of
+        # mini_batch_size * world rows, each rank processes the members it owns - bit-for-bit the sample sets, weights
+        # and RNG stream of a single process holding all envs (tools/storage.py:60-66, algo/ppo.py:64-119).
+        self.exact_sharding = False
 
     def update(self, rollouts, expert_dataset=None):
         pol = self.actor_critic
@@ -44,11 +48,17 @@ class PPO():
         T, N = rollouts.num_steps, rollouts.num_processes
         logstd = pol.base.logstd.tolist()
         act = pol.base.activation
+        world = world_size()
+        rank = dist.get_rank() if world > 1 else 0
+        exact = bool(self.exact_sharding) and world > 1
+        if exact and rollouts.shard != (rank, world):
+            raise RuntimeError("exact_sharding needs rollouts.set_shard(rank, world) on every rank")
+        self.optimizer.grad_scale = 1.0 if exact else None
 
         # advantage statistics over the whole rollout (algo/ppo.py:47-49); normalisation itself is fused into the loss
         stats = torch.zeros(4, dtype=torch.float64, device=dev)
         A.adv_stats(rollouts.returns, rollouts.value_preds, stats, T * N)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if world > 1:
             dist.all_reduce(stats[:3], op=dist.ReduceOp.SUM)   # {sum, sumsq, count} are additive across env shards
 
         obs_rows, met_rows = rollouts.flat("obs"), rollouts.flat("metrics")
@@ -56,54 +66,88 @@ class PPO():
         ret_rows, lp_rows = rollouts.flat("returns"), rollouts.flat("action_log_probs")
 
         B = self.mini_batch_size
+        Bg = B * world if exact else B            # rows one optimisation step averages over on this rank's scale
         use_bc = bool(expert_dataset)
         w_act = (1.0 - self.gamma) if use_bc else 1.0
         acc = torch.zeros(4, dtype=torch.float64, device=dev)
         n_updates = 0
         n_bc_rows = 0
+
+        def epoch_batches():   # one fresh permutation per epoch (tools/storage.py:60-63)
+            if exact:
+                return rollouts.sharded_minibatches(Bg)
+            return ((None, idx) for idx in rollouts.minibatch_indices(B))
+
         for _ in range(self.ppo_epoch):
-            for idx in rollouts.minibatch_indices(B):
-                Be = 0
+            for pos, idx in epoch_batches():
+                Bl = int(idx.shape[0])             # rows of this step on this rank (== B unless exact sharding)
+                Be = Be_norm = 0
                 e_act = None
                 if use_bc:   # algo/ppo.py:88-102: first batch of a fresh iterator over the expert loader
                     for e_batch in expert_dataset:
+                        if exact:     # every rank sees the same expert batch: take an equal contiguous share of its rows
+                            e_batch, Be_norm = _share_of(e_batch, rank, world)
                         e_obs, e_met, e_act_rows, e_idx, Be = expert_rows(e_batch, dev)
+                        Be_norm = Be_norm or Be
                         break
-                ws = eng.workspace(B + Be)
-                eng.load_inputs(obs_rows, met_rows, idx, B)
+                ws = eng.workspace(max(Bl + Be, 1))
+                if Bl:
+                    eng.load_inputs(obs_rows, met_rows, idx, Bl)
                 if Be:
-                    eng.load_inputs(e_obs, e_met, e_idx, Be, row0=B)
+                    eng.load_inputs(e_obs, e_met, e_idx, Be, row0=Bl)
                     if e_idx is None:
                         e_act = e_act_rows
                     else:   # device-resident expert table: gather the batch's action rows
                         e_act = ws.buf("e_act", ws.rows, 2)
                         A.gather_rows(e_act_rows, e_idx, e_act, Be, 2, 2)
-                a_b = ws.buf("act", ws.rows, 2); vo_b = ws.buf("vold", ws.rows); r_b = ws.buf("ret", ws.rows)
-                lp_b = ws.buf("olp", ws.rows)
-                A.gather_rows(act_rows, idx, a_b, B, 2, 2)
-                A.gather_rows(vp_rows, idx, vo_b, B, 1, 1)
-                A.gather_rows(ret_rows, idx, r_b, B, 1, 1)
-                A.gather_rows(lp_rows, idx, lp_b, B, 1, 1)
-                head = eng.forward(B + Be, training=True)
-                d_head = ws.buf("dhead", ws.rows, 4)
-                A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats, d_head, None, None, acc, B, logstd, act,
-                           float(self.clip_param), float(self.value_loss_coef), float(w_act), 0)
-                if Be:
-                    A.ppo_loss(head[B:], e_act, None, None, None, None, None, d_head[B:], None, None, acc, Be, logstd, act,
-                               0.0, 0.0, float(self.gamma), 1)
-                    n_bc_rows += Be
-                eng.backward(B + Be, d_head)
+                if Bl + Be:
+                    a_b = ws.buf("act", ws.rows, 2); vo_b = ws.buf("vold", ws.rows); r_b = ws.buf("ret", ws.rows)
+                    lp_b = ws.buf("olp", ws.rows)
+                    if Bl:
+                        A.gather_rows(act_rows, idx, a_b, Bl, 2, 2)
+                        A.gather_rows(vp_rows, idx, vo_b, Bl, 1, 1)
+                        A.gather_rows(ret_rows, idx, r_b, Bl, 1, 1)
+                        A.gather_rows(lp_rows, idx, lp_b, Bl, 1, 1)
+                    head = eng.forward(Bl + Be, training=True)
+                    d_head = ws.buf("dhead", ws.rows, 4)
+                    if Bl:
+                        A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats, d_head, None, None, acc, Bl, logstd, act,
+                                   float(self.clip_param), float(self.value_loss_coef), float(w_act), 0,
+                                   clipped_value=self.use_clipped_value_loss, norm=Bg if exact else None)
+                    if Be:
+                        A.ppo_loss(head[Bl:], e_act, None, None, None, None, None, d_head[Bl:], None, None, acc, Be, logstd, act,
+                                   0.0, 0.0, float(self.gamma), 1, norm=Be_norm if exact else None)
+                    eng.backward(Bl + Be, d_head, reducer=self.optimizer.reducer)
+                else:            # this rank owns no member of the global minibatch: it contributes a zero gradient
+                    eng.flat.begin_backward()
+                n_bc_rows += Be_norm if exact else Be
                 self.optimizer.step()
                 eng.dirty = True
                 eng.sync_params()
                 n_updates += 1
 
+        if world > 1:       # loss sums are additive across ranks (algo/ppo.py:128-141 reports global-batch means)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
         a = acc.cpu().tolist()                      # the only host synchronisation of the update
-        value_loss = a[0] / (B * n_updates)
-        gail_action_loss = a[1] / (B * n_updates)
-        bc_loss = (a[2] / n_bc_rows) if n_bc_rows else 0.0
+        rows = (Bg if exact else B * world) * n_updates
+        value_loss = a[0] / rows
+        gail_action_loss = a[1] / rows
+        n_bc = n_bc_rows if exact else n_bc_rows * world
+        bc_loss = (a[2] / n_bc) if n_bc else 0.0
         action_loss = self.gamma * bc_loss + (1 - self.gamma) * gail_action_loss if use_bc else gail_action_loss
         entropy = sum(0.5 + 0.5 * math.log(2 * math.pi) + v for v in logstd)
         if self.gamma is not None:
             self.gamma *= self.decay
         return value_loss, action_loss, entropy, bc_loss, gail_action_loss, self.gamma, logstd[0], logstd[1]
+
+
+def _share_of(batch, rank: int, world: int):
+    """Rank's contiguous share of an expert batch every rank holds a copy of -> (batch share, global row count)."""
+    from .expert import DeviceBatch
+    if isinstance(batch, DeviceBatch):
+        n = batch.batch_rows
+        lo, hi = n * rank // world, n * (rank + 1) // world
+        return DeviceBatch(batch.obs_table, batch.metrics_table, batch.actions_table, batch.idx[lo:hi].contiguous()), n
+    n = int(batch[0].shape[0])
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    return tuple(t[lo:hi] for t in batch), n

@@ -17,6 +17,7 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
+import torch.distributed as dist
 import torch.nn as nn
 
 from . import _abi as A
@@ -24,7 +25,7 @@ from . import engine as E
 from ._abi import LDF, S2D_PER_SAMPLE, EPI_BIAS_LRELU, EPI_MASK, EPI_STORE
 from .model import _Holder, _conv_seq, N_METRIC_FEAT
 from .expert import DeviceBatch, expert_rows
-from .optim import FusedClipAdam
+from .optim import FusedClipAdam, world_size
 from .running_mean_std import RunningMeanStd
 
 TAIL = N_METRIC_FEAT + 2      # metric features + action columns of trunk.0 (algo/wdgail.py:26-29)
@@ -47,6 +48,9 @@ class CriticEngine:
         dev = self.flat.flat.device
         if dev.type != "cuda" and not getattr(A, "EMULATED", False):
             raise RuntimeError("gail_carla_b200.Discriminator runs on CUDA only: move it to a CUDA device (no CPU fallback)")
+        ver = self.flat.version()
+        if ver != getattr(self, "_version", None):     # torch code wrote a parameter in place since the last preparation
+            self.dirty, self._version = True, ver
         if moved or self.dirty or self.w1 is None or self.w1.device != dev:
             if self.w1 is None or self.w1.device != dev:
                 self.w1 = torch.zeros(self.hidden, LDF, dtype=torch.float32, device=dev)
@@ -92,9 +96,11 @@ class CriticEngine:
         self.conv.forward(self.ws, rows, training=training)
         return self.trunk_forward(rows)
 
-    def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0) -> None:
+    def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0, norm=None, reducer=None) -> None:
         """Rows [0,B) expert, [B,2B) policy already loaded.  Builds the mix-up rows, runs forward + the full
-        backward (Wasserstein part + gradient penalty) and leaves the gradients in the flat buffer."""
+        backward (Wasserstein part + gradient penalty) and leaves the gradients in the flat buffer.
+        `norm`: rows the batch means run over (default B; the global minibatch size when B is one rank's share of it).
+        `reducer` (optim.GradReducer) is told when slices of the gradient buffer are final (multi-GPU overlap)."""
         ws, P, G, H_ = self.ws, self.flat.p, self.flat.g, self.hidden
         R = 3 * B
         # ---- forward over expert | policy | mix-up (algo/wdgail.py:116,121,66-82)
@@ -102,9 +108,9 @@ class CriticEngine:
         self.tail_features(B, 0); self.tail_features(B, B); self.tail_features(B, 2 * B, mix_from=(0, B, alpha))
         d = self.forward(R, training=True)
         dd = ws.buf("dd", ws.rows)
-        A.disc_loss_seed(d, dd, acc, B)                                   # acc[0:4]; seeds -/+tanh'/B and 1
+        A.disc_loss_seed(d, dd, acc, B, norm)                             # acc[0:4]; seeds -/+tanh'/B and 1
         # ---- backward
-        self.flat.grad.zero_()
+        self.flat.begin_backward()
         dA = ws.grads()
         H = ws.buf("H", ws.rows, LDH)
         dH = ws.buf("dH", ws.rows, LDH)
@@ -120,7 +126,7 @@ class CriticEngine:
         self.conv.backward_data(ws, R)
         # ---- gradient penalty: g = dD/dx on the mix-up rows, u = d gp/d g, second-order forward chain in place
         self.conv.input_grad(ws, B, 2 * B)
-        A.grad_penalty(dA[0][2 * B:], ws.X0[2 * B:], acc[4:], B, S2D_PER_SAMPLE, lambda_, E.INV_STD)
+        A.grad_penalty(dA[0][2 * B:], ws.X0[2 * B:], acc[4:], B, S2D_PER_SAMPLE, lambda_, E.INV_STD, norm)
         self.conv.forward_masked(ws, B, 2 * B)
         ws.F[2 * B:R, E.FEAT:].zero_()                                     # penalty gradient of the tail columns is 0
         t = ws.buf("v5", ws.rows, LDH)
@@ -131,11 +137,16 @@ class CriticEngine:
         E.linear_wgrad(ws, "w1d", dH, LDH, ws.F, LDF, self.dw1, LDF, H_, LDF, R)
         A.unprep_fc1_wgrad(self.dw1, 1, G("trunk.0.weight"), H_, TAIL, LDF)
         A.colsum(dH, LDH, 2 * B, H_, G("trunk.0.bias"))
+        if reducer is not None:      # embedding + trunk are final; only the convolution weight gradients remain
+            reducer.ready(self.flat, *self.flat.span("metrics_processor.road_option_embedding.weight"))
         self.conv.backward_params(ws, R, 2 * B)
 
 
 class Discriminator(nn.Module):
-    N_STAGING = 3     # device staging sets of the expert-batch prefetch ring (prefetch depth N_STAGING - 1)
+    # device staging sets of the expert-batch prefetch ring (prefetch depth N_STAGING - 1).  Three sets were measured
+    # against two (profiles/r02_bench_c4_n1_round1_binary.json: e2e 1581 vs 1600 ms/step, i.e. nothing) and cost
+    # another 1.8 GB of HBM per set at B=4096 fp32, so two it is.
+    N_STAGING = 2
     def __init__(self, state_shape, metrics_space, action_space, hidden_dim, device, lr, eps, betas, max_grad_norm=None):
         super(Discriminator, self).__init__()
         if tuple(state_shape) != (3, 192, 192) or metrics_space.shape[0] != 4 or action_space.shape[0] != 2:
@@ -167,13 +178,36 @@ class Discriminator(nn.Module):
         return self.engine.flat.flat.device
 
     def _to_dev(self, *ts):
+        """fp32 on the device; uint8 observations (bytes standing for b/255, see storage.ByteObs) stay uint8."""
         dev = self._dev()
-        return [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in ts]
+        out = []
+        for t in ts:
+            if t.dtype == torch.uint8:
+                out.append(t.as_subclass(torch.Tensor).to(dev, non_blocking=True).contiguous())
+            else:
+                out.append(t.to(dev, torch.float32, non_blocking=True).contiguous())
+        return out
 
-    # ---- algo/wdgail.py:40-54 (forward only; gp=True has no meaning without autograd)
+    # ---- algo/wdgail.py:40-54
     def forward(self, state, metrics, action, gp=False):
+        """gp=False: critic output [B,1] (no autograd graph).  gp=True (algo/wdgail.py:51-52): ``(output,
+        state_transformed, metrics_transformed, action_transformed)`` where ``state_transformed`` is a leaf copy of the
+        raw input image with ``requires_grad`` and ``output`` is differentiable w.r.t. it to first order
+        (``autograd.grad(output, state_transformed, ones)`` = the dD/dx of algo/wdgail.py:85-91, computed by the engine's
+        dgrad chain).  The second-order graph the reference builds with ``create_graph=True`` does not exist here -
+        ``compute_grad_pen`` / ``update`` use the hand-derived second-order pass instead."""
         if gp:
-            raise NotImplementedError("the autograd handles of forward(gp=True) do not exist here; use compute_grad_pen")
+            eng = self.engine
+            eng.sync_params()
+            state_d, metrics_d, action_d = self._to_dev(state, metrics, action)
+            if state_d.dtype == torch.uint8:
+                state_d = state_d.float().div_(255.0)
+            state_t = state_d.clone().requires_grad_(True)
+            out = _CriticOfImage.apply(self, state_t, metrics_d, action_d)
+            B = state_t.shape[0]
+            with torch.no_grad():
+                feats = eng.ws.F[:B, E.FEAT:E.FEAT + N_METRIC_FEAT].clone()
+            return out, state_t, feats, action_d.clone()
         with torch.no_grad():
             eng = self.engine
             eng.sync_params()
@@ -246,8 +280,8 @@ class Discriminator(nn.Module):
                 ready[k].record(main)
                 return batch, idx
             bufs = self._stage_bufs[k]
-            if bufs is None or any(b.shape != t.shape for b, t in zip(bufs, batch)):
-                bufs = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in batch]
+            if bufs is None or any(b.shape != t.shape or b.dtype != _stage_dtype(t) for b, t in zip(bufs, batch)):
+                bufs = [torch.empty(t.shape, dtype=_stage_dtype(t), device=dev) for t in batch]
                 self._stage_bufs[k] = bufs
                 self._copy_stream.wait_stream(main)          # fresh buffers: order after whatever main was doing
             if consumed[k] is not None:
@@ -260,7 +294,8 @@ class Discriminator(nn.Module):
                 ready[k].record(self._copy_stream)
                 if trace is not None:
                     c1 = torch.cuda.Event(enable_timing=True); c1.record(self._copy_stream)
-                    trace.append(("copy", c0, c1))
+                    if len(trace) < 4096:          # diagnostics only: never grow without bound
+                        trace.append(("copy", c0, c1))
             return bufs, idx
 
         def releaser(k):
@@ -304,18 +339,31 @@ class Discriminator(nn.Module):
         eng.sync_params()
         dev = self._dev()
         B = expert_loader.batch_size
+        world = world_size()
+        rank = dist.get_rank() if world > 1 else 0
+        # exact multi-GPU mode (see PPO.exact_sharding): `expert_loader` yields the same GLOBAL batches of B rows on every
+        # rank, the policy minibatch is a global one, and this rank processes the positions whose env it owns - expert row
+        # i, policy row i and alpha[i] stay paired exactly as algo/wdgail.py:66-80 pairs them
+        exact = bool(getattr(self, "exact_sharding", False)) and world > 1
+        if exact and rollouts.shard != (rank, world):
+            raise RuntimeError("exact_sharding needs rollouts.set_shard(rank, world) on every rank")
+        self.optimizer.grad_scale = 1.0 if exact else None
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
         acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
         # Mix-up coefficients (algo/wdgail.py:66: torch.rand(B,1,1,1) per batch on the CPU default generator).  All
         # host->device transfers share one DMA queue, so a small per-batch upload on the compute stream would queue
-        # behind the 1.8 GB expert prefetch and stall compute; when the number of batches is known the draws are made in
+        # behind the expert prefetch and stall compute; when the number of batches is known the draws are made in
         # the reference's order up front and uploaded once.
-        pairs = zip(expert_loader, rollouts.minibatch_indices(B))
+        if exact:
+            pairs = ((_rows_of(e, pos), (pos, idx)) for e, (pos, idx) in zip(expert_loader, rollouts.sharded_minibatches(B)))
+        else:
+            pairs = zip(expert_loader, ((None, idx) for idx in rollouts.minibatch_indices(B)))
         alphas = None
         if hasattr(expert_loader, "__len__") and dev.type == "cuda":
             first = next(pairs, None)          # advances both iterators exactly like the first zip step (draws randperm)
-            n_batches = min(len(expert_loader), (rollouts.num_steps * rollouts.num_processes) // B) if first is not None else 0
+            n_rollout = rollouts.num_steps * rollouts.num_processes * (world if exact else 1)
+            n_batches = min(len(expert_loader), n_rollout // B) if first is not None else 0
             if n_batches:
                 host = torch.empty(n_batches, B, pin_memory=True)
                 for i in range(n_batches):
@@ -324,23 +372,32 @@ class Discriminator(nn.Module):
             import itertools
             pairs = itertools.chain([first], pairs) if first is not None else iter(())
         with torch.no_grad():
-            for i_batch, (e_batch, idx, release) in enumerate(self._prefetched(pairs)):
+            for i_batch, (e_batch, (pos, idx), release) in enumerate(self._prefetched(pairs)):
                 e_obs, e_met, e_act, e_idx, e_rows = expert_rows(e_batch, dev)
-                if e_rows != B:
+                Bl = int(idx.shape[0])
+                if e_rows != Bl or (not exact and Bl != B):
                     raise ValueError("expert batches must all have expert_loader.batch_size rows (drop_last=True)")
-                eng.workspace(3 * B)
-                eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
-                release()
-                eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
                 if alphas is not None and i_batch < alphas.shape[0]:
                     alpha = alphas[i_batch]
                 else:
                     alpha = self._upload_alpha(torch.rand(B, 1, 1, 1).view(B))
-                eng.update_step(B, alpha, acc)
+                if exact:
+                    alpha = alpha[pos.to(alpha.device)].contiguous()
+                if Bl:
+                    eng.workspace(3 * Bl)
+                    eng.load_inputs(e_obs, e_met, e_act, e_idx, Bl, 0)
+                    release()
+                    eng.load_inputs(obs_rows, met_rows, act_rows, idx, Bl, Bl)
+                    eng.update_step(Bl, alpha, acc, norm=B if exact else None, reducer=self.optimizer.reducer)
+                else:              # this rank owns no member of the global minibatch: zero gradient, still all-reduces
+                    release()
+                    eng.flat.begin_backward()
                 self.optimizer.step()
                 eng.dirty = True
                 eng.sync_params()
-                n += B
+                n += B if exact else Bl * world
+        if world > 1:           # the tuple reports global-batch means (algo/wdgail.py:147)
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
         s_de, s_dp, s_te, s_tp, s_gp = acc[:5].cpu().tolist()   # single read-back per update
         wd = s_te - s_tp
         gp = 10.0 * s_gp
@@ -352,6 +409,7 @@ class Discriminator(nn.Module):
         eng.sync_params()
         dev = self._dev()
         B = expert_loader.batch_size
+        world = world_size()
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
         acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
@@ -365,6 +423,9 @@ class Discriminator(nn.Module):
                 d = eng.forward(2 * B)
                 A.disc_loss_seed(d, eng.ws.buf("dd", eng.ws.rows), acc, B)     # only the tanh sums are used here
                 n += B
+        if world > 1:           # every rank evaluated its own shard: report the mean over all of them
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+            n *= world
         _, _, s_te, s_tp = acc[:4].cpu().tolist()
         if n == 0:
             return 0, 0, 0
@@ -394,3 +455,55 @@ class Discriminator(nn.Module):
                 eng.tail_features(B, 0)
                 d = eng.forward(B)
                 A.reward_epilogue(d, out[s:], B)
+
+
+def _stage_dtype(t: torch.Tensor):
+    """Staging dtype of an expert-batch tensor: uint8 observations stay bytes, everything else is fp32."""
+    return torch.uint8 if t.dtype == torch.uint8 else torch.float32
+
+
+def _rows_of(batch, pos: torch.Tensor):
+    """Rows `pos` (CPU int64) of an expert batch in either form (exact multi-GPU mode)."""
+    if isinstance(batch, DeviceBatch):
+        return DeviceBatch(batch.obs_table, batch.metrics_table, batch.actions_table, batch.idx[pos.to(batch.idx.device)].contiguous())
+    return tuple(t[pos] for t in batch)
+
+
+class _CriticOfImage(torch.autograd.Function):
+    """Autograd bridge of ``Discriminator.forward(gp=True)``: D(x) with a first-order backward dD/dx through the engine's
+    dgrad chain (algo/wdgail.py:85-91 with create_graph=False).  The workspace holds the activations, so backward must
+    run before the next forward of this critic."""
+
+    @staticmethod
+    def forward(ctx, disc, state, metrics, action):
+        eng = disc.engine
+        B = state.shape[0]
+        eng.workspace(B)
+        eng.load_inputs(state.detach().contiguous(), metrics, action, None, B, 0)
+        eng.tail_features(B, 0)
+        out = eng.forward(B, training=True)[:B].clone().view(B, 1)
+        eng.forward_serial = getattr(eng, "forward_serial", 0) + 1
+        ctx.disc, ctx.B, ctx.serial = disc, B, eng.forward_serial
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        disc, B = ctx.disc, ctx.B
+        eng = disc.engine
+        if eng.forward_serial != ctx.serial:
+            raise RuntimeError("forward(gp=True): backward must run before the next forward pass of this Discriminator")
+        ws, P, H_ = eng.ws, eng.flat.p, eng.hidden
+        with torch.no_grad():
+            dA = ws.grads()
+            dd = ws.buf("dd", ws.rows)
+            dd[:B].copy_(g_out.reshape(B).to(dd.device, torch.float32))
+            H = ws.buf("H", ws.rows, LDH); dH = ws.buf("dH", ws.rows, LDH)
+            A.small_linear_bwd(H, LDH, P("trunk.2.weight"), dd, 1, dH, LDH, None, None, B, 0, 1, H_, E.SLOPE)
+            A.linear_dgrad(dH, LDH, eng.w1, LDF, dA[4], E.FEAT, B, E.FEAT, H_, mask_src=ws.F, ldm=LDF, slope=E.SLOPE,
+                           mask_bits=ws.mbits[4])
+            eng.conv.backward_data(ws, B)
+            eng.conv.input_grad(ws, B, 0)
+            # dX0 [B,96,96,(dy,dx,c4)] in normalised space -> d/d raw image [B,3,192,192] (x 1/std, drop the pad channel)
+            g = dA[0][:B].view(B, 96, 96, 2, 2, 4)[..., :3].permute(0, 5, 1, 3, 2, 4).reshape(B, 3, 192, 192)
+            g = g * torch.tensor(E.INV_STD, device=g.device).view(1, 3, 1, 1)
+        return None, g, None, None

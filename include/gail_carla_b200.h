@@ -20,10 +20,13 @@
 extern "C" {
 #endif
 
-#define GC_ABI_VERSION 1
+#define GC_ABI_VERSION 2
 
 const char* gc_last_error_string(void);
 int gc_abi_version(void);
+/* sha256 of the sources + flags this binary was built from (gail_carla_b200/build.py); the loader refuses a binary whose
+ * digest differs from the source tree next to it. */
+const char* gc_build_digest(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rollout maths (HBM-bound)
@@ -46,13 +49,17 @@ int gc_adv_normalize(const float* returns, const float* value_preds, const doubl
  * head_out [B,4] = {value, mu0_raw, mu1_raw, pad}; actions [B,2]; the scalar columns are [B].
  * mode 0 PPO: d_head_out = d(value_coef*value_loss + action_weight*action_loss)/d head_out.  Advantages come from `adv`
  *             when non-null, else are formed in-kernel as ((returns-value_old)-mean)/(std+1e-5) from adv_stats.
+ *             clipped_value != 0: 0.5*max((v-R)^2, (v_clipped-R)^2) (algo/ppo.py:104-111); 0: 0.5*(R-v)^2 (:112-113).
  * mode 1 BC : d_head_out = d(action_weight * -mean(logp))/d head_out.
  * mode 2    : forward only.
+ * inv_norm > 0 replaces 1/B as the weight of one sample in the batch means (a rank that holds B rows of a global
+ * minibatch of B_total rows passes 1/B_total and the per-rank gradients are summed); <= 0 selects 1/B.
  * out_value / out_logp (nullable) [B].  loss_acc (nullable) double[3] += {sum 0.5*max(.)^2 terms, sum -min(surr), sum -logp}. */
 int gc_ppo_loss_fwd_bwd(const float* head_out, const float* actions, const float* old_logp, const float* value_old,
                         const float* returns, const float* adv, const double* adv_stats, float* d_head_out,
                         float* out_value, float* out_logp, double* loss_acc, int B, float logstd0, float logstd1,
-                        int activation, float clip, float value_coef, float action_weight, int mode, void* stream);
+                        int activation, float clip, float value_coef, float action_weight, int mode, int clipped_value,
+                        float inv_norm, void* stream);
 
 /* Policy.act - tools/model.py:25-36.  noise (nullable) [B,2] standard normal draws; null => deterministic. */
 int gc_policy_act(const float* head_out, const float* noise, float* value, float* action, float* logp, int B, float logstd0,
@@ -102,14 +109,15 @@ int gc_small_linear_bwd(const float* x, long ldx, const float* w, const float* d
 
 /* Discriminator loss seeds - algo/wdgail.py:116-131.  d [3B] = {expert, policy, mixup} critic outputs.
  * dd[0:B] = -(1-tanh^2)/B, dd[B:2B] = +(1-tanh^2)/B, dd[2B:3B] = 1 (seed of dD/dx for the penalty).
- * acc double[4] += {sum d_e, sum d_p, sum tanh d_e, sum tanh d_p}. */
-int gc_disc_loss_seed(const float* d, float* dd, double* acc, int B, void* stream);
+ * acc double[4] += {sum d_e, sum d_p, sum tanh d_e, sum tanh d_p}.  inv_norm as for gc_ppo_loss_fwd_bwd (replaces 1/B). */
+int gc_disc_loss_seed(const float* d, float* dd, double* acc, int B, float inv_norm, void* stream);
 
 /* Gradient penalty - algo/wdgail.py:93-97.  g [B,per_sample] = dD/dx_n w.r.t. the *normalised* s2d input; the reference
  * differentiates w.r.t. the raw input, g_raw = g * s_c with s_c = 1/std_c and c = element index & 3 (s3 = 0 for the pad
- * channel).  acc[0] += sum_b (||g_raw,b||-1)^2;  u = d(lambda*mean_b(||g_raw,b||-1)^2)/dg, same layout as g. */
+ * channel).  acc[0] += sum_b (||g_raw,b||-1)^2;  u = d(lambda*mean_b(||g_raw,b||-1)^2)/dg, same layout as g; the mean is
+ * over 1/inv_norm samples when inv_norm > 0, else over B. */
 int gc_grad_penalty(const float* g, float* u, double* acc, int B, long per_sample, float lambda_, float s0, float s1, float s2,
-                    void* stream);
+                    float inv_norm, void* stream);
 
 /* reward = -log(1 - sigmoid(d)) - algo/wdgail.py:185-186. */
 int gc_reward_epilogue(const float* d, float* reward, long n, void* stream);
@@ -141,12 +149,17 @@ int gc_unprep_fc1_wgrad(const float* part, int splits, float* dw, int out, int t
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser: clip_grad_norm_ + Adam - algo/ppo.py:115-119, algo/wdgail.py:140-145
  * ---------------------------------------------------------------------------------------------------------- */
-/* sumsq double[1] += sum g^2 */
-int gc_grad_sumsq(const float* grad, long n, double* sumsq, void* stream);
-/* g *= min(1, max_norm/(sqrt(sumsq)+1e-6)); Adam step (torch.optim.Adam, no amsgrad/weight decay).
- * bias_corr1 = 1-beta1^t, bias_corr2 = 1-beta2^t.  max_norm < 0 disables clipping. */
+/* sumsq double[1] += sum (grad_scale*g)^2.  grad_scale = 1/world_size after a NCCL SUM all-reduce of per-rank mean
+ * gradients (the global-batch gradient of algo/ppo.py:115), 1 otherwise. */
+int gc_grad_sumsq(const float* grad, long n, float grad_scale, double* sumsq, void* stream);
+/* g' = grad_scale*g * min(1, max_norm/(sqrt(sumsq)+1e-6)); Adam step with g' (torch.optim.Adam, no amsgrad/weight decay).
+ * bias_corr1 = 1-beta1^t, bias_corr2 = 1-beta2^t.  max_norm < 0 disables clipping.  zero_grad != 0 writes 0 over each
+ * gradient element after reading it (optimizer.zero_grad() of the next minibatch, algo/ppo.py:115, without another pass).
+ * dev_hyper (nullable) device float[3] = {lr, bias_corr1, bias_corr2} overrides the by-value arguments, so a captured CUDA
+ * graph of the minibatch step can be replayed while the step count and the learning-rate schedule advance. */
 int gc_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, long n, const double* sumsq, float max_norm,
-                 float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2, void* stream);
+                 float lr, float beta1, float beta2, float eps, float bias_corr1, float bias_corr2, float grad_scale,
+                 int zero_grad, const float* dev_hyper, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense contractions on tcgen05 tensor cores (TF32 in, fp32 accumulate in TMEM, TMA-fed implicit GEMM)

@@ -79,7 +79,7 @@ def _head_tail(head, actions, logstd, activation):
 
 @torch.enable_grad()
 def ppo_loss(head_out, actions, old_logp, value_old, returns, adv, adv_stats_, d_head, out_value, out_logp, loss_acc, B,
-             logstd, activation, clip, value_coef, action_weight, mode):
+             logstd, activation, clip, value_coef, action_weight, mode, clipped_value=True, norm=None):
     h = head_out.view(-1, 4)[:B].detach().clone().requires_grad_(mode != 2)
     a = actions.view(-1, 2)[:B]
     v, _, _, logp = _head_tail(h, a, logstd, activation)
@@ -98,13 +98,17 @@ def ppo_loss(head_out, actions, old_logp, value_old, returns, adv, adv_stats_, d
             A = ((R - vo) - mean) * inv
         ratio = torch.exp(logp - olp)
         neg_min = -torch.min(ratio * A, torch.clamp(ratio, 1 - clip, 1 + clip) * A)
-        vc = vo + (v - vo).clamp(-clip, clip)
-        vl = 0.5 * torch.max((v - R) ** 2, (vc - R) ** 2)
-        (value_coef * vl.mean() + action_weight * neg_min.mean()).backward()
+        if clipped_value:
+            vc = vo + (v - vo).clamp(-clip, clip)
+            vl = 0.5 * torch.max((v - R) ** 2, (vc - R) ** 2)
+        else:
+            vl = 0.5 * (R - v) ** 2
+        nb = B if norm is None else norm
+        (value_coef * vl.sum() / nb + action_weight * neg_min.sum() / nb).backward()
         if loss_acc is not None:
             loss_acc[0] += vl.detach().double().sum(); loss_acc[1] += neg_min.detach().double().sum()
     else:
-        (action_weight * (-logp).mean()).backward()
+        (action_weight * (-logp).sum() / (B if norm is None else norm)).backward()
         if loss_acc is not None:
             loss_acc[2] += (-logp).detach().double().sum()
     g = h.grad.clone()
@@ -204,23 +208,24 @@ def small_linear_bwd(x, ldx, w, dy, lddy, dx, lddx, dw, db, B, B_params, N, K, s
             db.view(-1)[:N].add_(DY[:B_params].sum(0))
 
 
-def disc_loss_seed(d, dd, acc, B):
+def disc_loss_seed(d, dd, acc, B, norm=None):
     d = d.view(-1)
     te, tp = torch.tanh(d[:B]), torch.tanh(d[B:2 * B])
     o = dd.view(-1)
-    o[:B] = -(1 - te * te) / B
-    o[B:2 * B] = (1 - tp * tp) / B
+    nb = B if norm is None else norm
+    o[:B] = -(1 - te * te) / nb
+    o[B:2 * B] = (1 - tp * tp) / nb
     o[2 * B:3 * B] = 1.0
     acc[0] += d[:B].double().sum(); acc[1] += d[B:2 * B].double().sum()
     acc[2] += te.double().sum(); acc[3] += tp.double().sum()
 
 
-def grad_penalty(g, u, acc, B, per_sample, lambda_, scales):
+def grad_penalty(g, u, acc, B, per_sample, lambda_, scales, norm=None):
     G = g.reshape(-1)[:B * per_sample].view(B, -1, 4)
     s = torch.tensor([scales[0], scales[1], scales[2], 0.0])
     nrm = torch.sqrt(((G * s).double() ** 2).sum((1, 2))).float()
     acc[0] += ((nrm - 1).double() ** 2).sum()
-    coef = torch.where(nrm > 0, lambda_ * 2 * (nrm - 1) / (B * nrm), torch.zeros_like(nrm))
+    coef = torch.where(nrm > 0, lambda_ * 2 * (nrm - 1) / ((B if norm is None else norm) * nrm), torch.zeros_like(nrm))
     u.view(-1)[:B * per_sample] = (coef.view(B, 1, 1) * (s * s) * G).reshape(-1)
 
 
@@ -291,18 +296,24 @@ def unprep_fc1_wgrad(part, splits, dw, out, tail, ld):
     d[:, 25600:] = s[:, 25600:25600 + tail]
 
 
-def grad_sumsq(grad, n, sumsq):
-    sumsq[0] += (grad.reshape(-1)[:n].double() ** 2).sum()
+def grad_sumsq(grad, n, sumsq, grad_scale=1.0):
+    sumsq[0] += ((grad.reshape(-1)[:n].double() * grad_scale) ** 2).sum()
 
 
-def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2):
-    p, g, m, v = (t.view(-1)[:n] for t in (param, grad, exp_avg, exp_avg_sq))
+def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2, grad_scale=1.0,
+              zero_grad=False, dev_hyper=None):
+    if dev_hyper is not None:
+        lr, bc1, bc2 = (float(x) for x in dev_hyper[:3])
+    p, g0, m, v = (t.view(-1)[:n] for t in (param, grad, exp_avg, exp_avg_sq))
+    g = g0 * grad_scale
     if max_norm is not None and max_norm >= 0:
         total = torch.sqrt(sumsq[0]).float()
         g = g * torch.clamp(max_norm / (total + 1e-6), max=1.0)
     m.mul_(beta1).add_(g, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
     p.addcdiv_(m, v.sqrt() / math.sqrt(bc2) + eps, value=-lr / bc1)
+    if zero_grad:
+        g0.zero_()
 
 
 # ------------------------------------------------------------------ dense contractions

@@ -24,7 +24,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
     assert sorted(_abi.EXPORTS) == syms, "ctypes binding and header disagree on the entry points"
     lib.gc_abi_version.restype = ctypes.c_int
-    assert lib.gc_abi_version() == 1
+    assert lib.gc_abi_version() == 2
 
 
 def test_argument_errors_are_reported_not_thrown():
