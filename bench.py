@@ -43,10 +43,16 @@ CONFIGS = {
                  workload="per-rank share of configs[3] at 8 GPUs: 8 envs x 1024 steps, B=512"),
     "c4r4": dict(T=1024, N=16, B_ppo=1024, B_gail=1024, ppo_epoch=1, gail_epoch=1,
                  workload="per-rank share of configs[3] at 4 GPUs: 16 envs x 1024 steps, B=1024"),
+    # stock-PyTorch-on-CUDA yardstick (`gpu_baseline`): a shorter rollout with the batch sizes autograd's graphs allow
+    "g2048": dict(T=128, N=64, B_ppo=2048, B_gail=2048, ppo_epoch=1, gail_epoch=1, workload="64 envs x 128 steps, B=2048"),
+    "g1024": dict(T=128, N=64, B_ppo=1024, B_gail=1024, ppo_epoch=1, gail_epoch=1, workload="64 envs x 128 steps, B=1024"),
+    "g512": dict(T=128, N=64, B_ppo=512, B_gail=512, ppo_epoch=1, gail_epoch=1, workload="64 envs x 128 steps, B=512"),
     "tiny": dict(T=64, N=8, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1, workload="tiny: 8 envs x 64 steps, B=128"),
     # the bounded sample the CPU arm runs: configs[0] verbatim
     "c1": dict(T=128, N=1, B_ppo=128, B_gail=128, ppo_epoch=1, gail_epoch=1,
                workload="configs[0]: 1 env x 128 steps, B=128"),
+    "c1b512": dict(T=512, N=1, B_ppo=512, B_gail=512, ppo_epoch=1, gail_epoch=1,
+                   workload="1 env x 512 steps, B=512 (batch-size bracket of the CPU sample)"),
 }
 
 
@@ -98,31 +104,46 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's CPU torch path for the same update, through the oracle restatement (oracle/ref_path.py, pinned
-    against the unmodified reference - the reference tree itself does not exist on the GPU box), all host threads,
-    on a bounded sample of the workload: configs[0] (1 env x 128 steps, B=128), one full update per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+class _DeviceLoader:
+    """Expert loader whose batches already live on `device` (yardstick runs only)."""
+    def __init__(self, inner, device):
+        self.batch_size = inner.batch_size
+        self._b = [tuple(t.to(device) for t in b) for b in inner]
+    def __len__(self):
+        return len(self._b)
+    def __iter__(self):
+        return iter(self._b)
+
+
+def oracle_update_seconds(c, device="cpu", repeats=1):
+    """One full update (tools/learn.py:137-223,269 minus diagnostics) of config `c` through the oracle restatement -
+    the reference's own stock-PyTorch code path, function for function - on `device`; returns seconds per update.
+    device="cpu": torch CPU fp32 on all host threads (the reference arm / cpu_baseline).  device="cuda": the same
+    PyTorch code on this GPU with cuDNN / cuBLAS free to use TF32 (`gpu_baseline`: the like-for-like competitor of the
+    hand-written kernels; data resident on the device, nothing of this repo's package on that path)."""
     from gail_carla_b200 import synthetic
     from oracle import ref_path as O
-    torch.set_num_threads(os.cpu_count())
-    c = CONFIGS["c1"]
     T, N = c["T"], c["N"]
+    dev = torch.device(device)
+    torch.manual_seed(1)
+    pol, disc = O.init_policy_params(), O.init_disc_params()
+    pol = {k: v.to(dev) for k, v in pol.items()}; disc = {k: v.to(dev) for k, v in disc.items()}
+    padam = O.AdamState(pol, HP["lr"], HP["eps"], HP["betas"]); dadam = O.AdamState(disc, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"])
+    ro = NS(obs=torch.zeros(T + 1, N, 3, 192, 192, device=dev), metrics=torch.zeros(T + 1, N, 4, device=dev),
+            actions=torch.zeros(T, N, 2, device=dev), action_log_probs=torch.zeros(T, N, 1, device=dev),
+            value_preds=torch.zeros(T + 1, N, 1, device=dev), returns=torch.zeros(T + 1, N, 1, device=dev),
+            masks=torch.ones(T + 1, N, 1, device=dev), gail_rewards=torch.zeros(T, N, 1, device=dev),
+            rewards=torch.zeros(T, N, 1, device=dev), num_steps=T, num_processes=N)
+    synthetic.fill_rollout(ro, seed=11, chunk=max(1, 2048 // N))
+    loader = synthetic.SyntheticExpertLoader(T * N // c["B_gail"], c["B_gail"], seed=21)
+    if dev.type == "cuda":
+        loader = _DeviceLoader(loader, dev)
+    d = {k: getattr(ro, k) for k in ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks",
+                                    "gail_rewards", "rewards")}
 
     def one_update():
-        torch.manual_seed(1)
-        pol, disc = O.init_policy_params(), O.init_disc_params()
-        padam = O.AdamState(pol, HP["lr"], HP["eps"], HP["betas"]); dadam = O.AdamState(disc, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"])
-        ro = NS(obs=torch.zeros(T + 1, N, 3, 192, 192), metrics=torch.zeros(T + 1, N, 4), actions=torch.zeros(T, N, 2),
-                action_log_probs=torch.zeros(T, N, 1), value_preds=torch.zeros(T + 1, N, 1), returns=torch.zeros(T + 1, N, 1),
-                masks=torch.ones(T + 1, N, 1), gail_rewards=torch.zeros(T, N, 1), rewards=torch.zeros(T, N, 1),
-                num_steps=T, num_processes=N)
-        synthetic.fill_rollout(ro, seed=11)
-        loader = synthetic.SyntheticExpertLoader(T * N // c["B_gail"], c["B_gail"], seed=21)
-        d = {k: getattr(ro, k) for k in ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks",
-                                        "gail_rewards", "rewards")}
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         with torch.no_grad():
             d["value_preds"][-1] = O.policy_base(pol, d["obs"][-1], d["metrics"][-1], True, HP["logstd"])[0]
@@ -133,22 +154,84 @@ def run_reference(args):
         d["returns"] = O.gae_returns(d["gail_rewards"], d["value_preds"], d["masks"], HP["gamma"], HP["gae_lambda"])
         O.ppo_update(pol, padam, d, clip_param=HP["clip_param"], ppo_epoch=c["ppo_epoch"], mini_batch_size=c["B_ppo"],
                      value_loss_coef=HP["value_loss_coef"], max_grad_norm=HP["max_grad_norm"], logstd=HP["logstd"])
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
 
+    if dev.type == "cuda":
+        one_update()                      # warm-up: cuDNN algorithm selection, allocator growth
+    return sum(one_update() for _ in range(repeats)) / repeats
+
+
+def cpu_update_seconds(c):
+    return oracle_update_seconds(c, "cpu")
+
+
+def gpu_baseline_sample(dev):
+    """Stock PyTorch on the same B200 (BASELINE.md section 4 "also reported where cheap"): the oracle restatement of the
+    reference's update on CUDA tensors, cuDNN autotuned, TF32 allowed for convolutions and matmuls (the reference's own
+    GPU path runs that way under its torch version).  Largest batch whose double-backward graph fits next to the
+    resident rollout is tried first."""
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    out = None
+    try:
+        for name in ("g2048", "g1024", "g512"):
+            c = CONFIGS[name]
+            try:
+                torch.cuda.empty_cache()
+                t = oracle_update_seconds(c, dev, repeats=2)
+                out = {"value": c["T"] * c["N"] / t, "unit": "env-steps/s", "seconds_per_update": t, "kind": "port",
+                       "what": "oracle/ref_path.py (the reference's stock PyTorch update, function for function) on cuda: cuDNN "
+                               "autotuned, TF32 allowed, rollout + expert batches resident on the device",
+                       "sample": c["workload"] + "; env-steps/s is per-sample work, so the bounded sample stands for the full workload"}
+                break
+            except torch.cuda.OutOfMemoryError:
+                out = {"unavailable": f"{name}: out of memory"}
+                continue
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_reference(args):
+    """The reference's CPU torch path for the same update, through the oracle restatement (oracle/ref_path.py, pinned
+    against the unmodified reference - the reference tree itself does not exist on the GPU box), all host threads.
+    A step is a BOUNDED SAMPLE of the workload: one full update of configs[0] (1 env x 128 steps, B=128) - the line's
+    `config` names what actually ran (`config.workload`) and the workload it stands for (`config.sample_of`).  The
+    per-sample cost of the CPU path falls with the batch size, so one extra update at B=512 (`cpu_baseline_b512`) brackets
+    the extrapolation from B=128 to the GPU arm's B=4096."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    c = CONFIGS["c1"]
+    T, N = c["T"], c["N"]
     for _ in range(args.warmup):
-        one_update()
-    times = [one_update() for _ in range(args.steps)]
+        cpu_update_seconds(c)
+    times = [cpu_update_seconds(c) for _ in range(args.steps)]
     dt = sum(times) / len(times)
     v = T * N / dt
     cfg = CONFIGS[args.config]
+    b512 = None
+    if not args.no_b512:
+        c512 = CONFIGS["c1b512"]
+        t512 = cpu_update_seconds(c512)
+        b512 = {"value": c512["T"] * c512["N"] / t512, "unit": "env-steps/s", "seconds": t512, "cores": torch.get_num_threads(),
+                "kind": "port", "sample": "one full update on " + c512["workload"] + ", run once after the timed steps"}
     line = {"impl": "reference", "metric": "ppo_wdgail_update_env_steps_per_sec", "value": v, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "T": cfg["T"], "N": cfg["N"], "B_ppo": cfg["B_ppo"], "B_gail": cfg["B_gail"],
-                       "ppo_epoch": cfg["ppo_epoch"], "gail_epoch": cfg["gail_epoch"]},
+            "config": {"workload": c["workload"] + " - CPU-port sample; per-sample rate extrapolates to " + cfg["workload"],
+                       "sample_of": cfg["workload"], "T": c["T"], "N": c["N"], "B_ppo": c["B_ppo"], "B_gail": c["B_gail"],
+                       "ppo_epoch": c["ppo_epoch"], "gail_epoch": c["gail_epoch"]},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "one full update on " + c["workload"] + " (torch CPU fp32, all host threads); env-steps/s "
-                                       "is per-sample work so the bounded sample stands for the full workload"},
+                             "sample": "one full update on " + c["workload"] + " (torch CPU fp32, all host threads) per step; "
+                                       "env-steps/s is per-sample work, see cpu_baseline_b512 for the batch-size dependence"},
+            "cpu_baseline_b512": b512,
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -269,13 +352,86 @@ def hbm_microbench(A, dev, pk):
 
 def cpu_baseline_sample():
     """Oracle port timed on this box's host cores on a bounded sample (one update of configs[0]); rank 0, N=1 only."""
-    a = NS(warmup=0, steps=1, gpus=1, config="c1")
+    a = NS(warmup=0, steps=1, gpus=1, config="c1", no_b512=True)
     import io, contextlib
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         run_reference(a)
     line = json.loads(buf.getvalue().strip().splitlines()[-1])
     return line["cpu_baseline"]
+
+
+def multi_gpu_parity(dev, rank, world):
+    """Hardware check of the multi-GPU semantics: a small rollout of 2*world envs x 16 steps is
+    updated once (Discriminator.update + predict_reward + GAE + PPO.update, global minibatches of 32 rows) by `world`
+    ranks in exact-sharding mode, and rank 0 then replays the same update as ONE process on the concatenated envs
+    from the same seeds.  Reports the largest parameter / tuple / returns deviations between the two runs (the sharded
+    run sums per-rank partial gradients over NCCL, the replay sums them inside one wgrad launch - TF32 products, fp32
+    sums in a different order, and Adam's sign-like first steps turn a flipped ~0 gradient into a 2*lr difference)."""
+    import torch.distributed as dist
+    import gail_carla_b200 as G
+    from gail_carla_b200 import synthetic, optim
+    from gail_carla_b200.driver import update_iteration
+    T, Nl, Bglob = 16, 2, 32
+    N = Nl * world
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+
+    def build(n_envs, mb, seed=5):
+        torch.manual_seed(seed)
+        pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False).to(dev)
+        agent = G.PPO(pol, HP["clip_param"], 1, mb, HP["value_loss_coef"], dev, lr=HP["lr"], eps=HP["eps"], betas=HP["betas"],
+                      max_grad_norm=HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+        disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, dev, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
+                               HP["gail_max_grad_norm"]).to(dev)
+        return pol, agent, disc
+
+    full = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=dev, obs_dtype=torch.uint8)
+    synthetic.fill_rollout(full, seed=17)
+    loader = synthetic.SyntheticExpertLoader(2, Bglob, seed=23, obs_u8=True)      # the same global batches on every rank
+    keys = ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks", "gail_rewards", "rewards")
+
+    pol, agent, disc = build(Nl, Bglob // world)
+    agent.exact_sharding = disc.exact_sharding = True
+    ro = G.RolloutStorage(T, Nl, synthetic.OBS_SHAPE, (4,), (2,), device=dev, obs_dtype=torch.uint8)
+    for k in keys:
+        getattr(ro, k).copy_(getattr(full, k)[:, rank * Nl:(rank + 1) * Nl])
+    ro.set_shard(rank, world)
+    torch.manual_seed(99)
+    d_out, p_out = update_iteration(pol, agent, disc, ro, loader, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"], gail_epoch=1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    res = None
+    if rank == 0:
+        with optim.single_process():
+            pol1, agent1, disc1 = build(N, Bglob)
+            torch.manual_seed(99)
+            d1, p1 = update_iteration(pol1, agent1, disc1, full, loader, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"], gail_epoch=1)
+        torch.cuda.synchronize()
+
+        def pdiff(a, b):
+            mx = mean = 0.0
+            for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+                d = (x.float() - y.float()).abs()
+                mx = max(mx, float(d.max())); mean = max(mean, float(d.mean()))
+            return mx, mean
+        def tdiff(a, b):
+            a = [float("nan") if v is None else float(v) for v in a]; b = [float("nan") if v is None else float(v) for v in b]
+            return max((abs(x - y) / (1e-6 + abs(y)) for x, y in zip(a, b) if x == x and y == y), default=0.0)
+        pm, pa = pdiff(pol, pol1); dm, da = pdiff(disc, disc1)
+        ret = float((ro.returns - full.returns[:, :Nl]).abs().max())
+        res = {"config": f"{N} envs x {T} steps over {world} ranks (exact sharding), global minibatch {Bglob}, 2 critic + {T * N // Bglob} PPO steps, "
+                         "vs a one-process replay of the concatenated envs on rank 0",
+               "policy_params_max_abs_diff": pm, "policy_params_max_abs_diff_over_lr": pm / HP["lr"],
+               "policy_params_worst_tensor_mean_abs_diff_over_lr": pa / HP["lr"],
+               "critic_params_max_abs_diff": dm, "critic_params_max_abs_diff_over_lr": dm / HP["gail_lr"],
+               "critic_params_worst_tensor_mean_abs_diff_over_lr": da / HP["gail_lr"],
+               "disc_update_tuple_max_rel_diff": tdiff(d_out[0], d1[0]), "ppo_update_tuple_max_rel_diff": tdiff(p_out, p1),
+               "returns_max_abs_diff_rank0_shard": ret}
+    dist.barrier()
+    del full, ro, pol, agent, disc
+    from gail_carla_b200 import engine as E
+    E.release_workspaces()
+    return res
 
 
 def run_b200(args):
@@ -304,6 +460,7 @@ def run_b200(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     A.load_library()
+    parity_multi = multi_gpu_parity(dev, rank, world) if world > 1 else None
     prof = Profiler(A)
     pk = peaks()
     c = dict(CONFIGS[args.config])
@@ -319,10 +476,13 @@ def run_b200(args):
                   betas=HP["betas"], max_grad_norm=HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
     disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, dev, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
                            HP["gail_max_grad_norm"]).to(dev)
-    ro = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=dev)
+    u8 = args.obs_store == "u8"
+    # Observations are uint8/255 by construction (carla_env.py:134-138): the byte store is lossless.  --obs-store f32
+    # keeps the reference's fp32 layout (4x the HBM, PCIe and gather traffic).
+    ro = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=dev, obs_dtype=torch.uint8 if u8 else torch.float32)
     synthetic.fill_rollout(ro, seed=11 + rank, chunk=max(1, 4096 // N))
     n_batches = (T * N) // Bg
-    loader = synthetic.SyntheticExpertLoader(n_batches, Bg, seed=21 + rank, pin=True)
+    loader = synthetic.SyntheticExpertLoader(n_batches, Bg, seed=21 + rank, pin=True, obs_u8=u8)
     torch.manual_seed(100 + rank)             # minibatch permutations / mix-up alphas differ per shard
 
     def step():
@@ -362,13 +522,14 @@ def run_b200(args):
     host = {}
     try:
         for k in names:
-            host[k] = torch.empty(getattr(ro, k).shape, dtype=torch.float32, pin_memory=True)
-            host[k].copy_(getattr(ro, k))
+            src = ro.flat(k).view(getattr(ro, k).shape)          # plain tensor view (ByteObs -> uint8)
+            host[k] = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            host[k].copy_(src)
         pinned = True
     except RuntimeError:
-        host = {k: getattr(ro, k).cpu() for k in names}
+        host = {k: ro.flat(k).view(getattr(ro, k).shape).cpu() for k in names}
         pinned = False
-    h2d = sum(v.numel() * 4 for v in host.values()) + sum(t.numel() * 4 for b in loader for t in b)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + sum(t.numel() * t.element_size() for b in loader for t in b)
     result_host = torch.empty(T, N, 1, dtype=torch.float32, pin_memory=True)
 
     # Double-buffered upload: rollout i+1 is copied from pinned host memory into a second obs buffer while update i
@@ -380,11 +541,12 @@ def run_b200(args):
     # - insert() copies one time slice per env step while the simulator runs (tools/learn.py:111-133).  Every timed step
     # issues and completes one full rollout upload; the small tensors go on the compute stream.
     up_stream = torch.cuda.Stream(device=dev)
+    obs_plain = ro.flat("obs").view(ro.obs.shape)
     try:
-        obs_bufs = [ro.obs, torch.empty_like(ro.obs)]
+        obs_bufs = [obs_plain, torch.empty_like(obs_plain)]
         double = True
     except RuntimeError:                                   # no room for a second obs buffer: upload, then update
-        obs_bufs = [ro.obs, ro.obs]
+        obs_bufs = [obs_plain, obs_plain]
         double = False
     small = [k for k in names if k != "obs"]
     uploaded = [torch.cuda.Event(), torch.cuda.Event()]
@@ -472,14 +634,14 @@ def run_b200(args):
     dt_e2e = timed_e2e(args.steps)
     torch.cuda.synchronize()
     e2e = env_steps * args.steps / dt_e2e
-    h2d_rollout = sum(v.numel() * 4 for v in host.values())
+    h2d_rollout = sum(v.numel() * v.element_size() for v in host.values())
 
     # ---- same, with the (static) expert data set resident in HBM as the uint8 bytes its PNGs hold (SURVEY 8f row 3,
     # gail_carla_b200/expert.py): only the rollout crosses PCIe.  Reported next to `e2e`, not instead of it.
     e2e_res = None
     try:
         from gail_carla_b200.expert import DeviceExpertLoader, ExpertDataset
-        ds = ExpertDataset.from_tensors(torch.cat([(b[0] * 255.0).round().to(torch.uint8) for b in loader]),
+        ds = ExpertDataset.from_tensors(torch.cat([b[0] if b[0].dtype == torch.uint8 else (b[0] * 255.0).round().to(torch.uint8) for b in loader]),
                                         torch.cat([b[1] for b in loader]), torch.cat([b[2] for b in loader]))
         e2e_loader["l"] = InterleavedLoader(DeviceExpertLoader(ds, Bg, shuffle=False, drop_last=True, device=dev))
         del ds
@@ -545,6 +707,18 @@ def run_b200(args):
             del a_, b_
         except Exception as ex:   # pragma: no cover
             roof["tf32_cublas_sustained_tflops"] = None
+    gpu_base = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline:
+        # yardstick, measured last with every buffer of the product path released: stock PyTorch on this same GPU
+        del ro, loader, host, obs_bufs
+        from gail_carla_b200 import engine as E
+        E.release_workspaces()
+        try:
+            gpu_base = gpu_baseline_sample(dev)
+            if gpu_base and "value" in gpu_base:
+                gpu_base["speedup_of_value"] = value / gpu_base["value"]
+        except Exception as ex:   # pragma: no cover - the yardstick must never take the bench line down
+            gpu_base = {"unavailable": f"{type(ex).__name__}: {str(ex)[:160]}"}
     if rank == 0:
         cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
         line = {"metric": "ppo_wdgail_update_env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
@@ -552,7 +726,8 @@ def run_b200(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
                 "config": {"workload": c["workload"], "T": T, "N": N_total, "B_ppo": c["B_ppo"], "B_gail": c["B_gail"],
                            "ppo_epoch": c["ppo_epoch"], "gail_epoch": c["gail_epoch"], "envs_per_rank": N,
-                           "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % (ro.obs.numel() * 4 / 1e9),
+                           "obs_store": "uint8 bytes (lossless: observations are uint8/255 by construction)" if u8 else "fp32 (reference layout)",
+                           "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % (ro.obs.numel() * ro.obs.element_size() / 1e9),
                            "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce"},
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned,
@@ -560,6 +735,7 @@ def run_b200(args):
                                   "predict_reward + PPO.update of step i; one full rollout upload + all expert batches per timed step"},
                 "e2e_expert_resident": e2e_res,
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm_kernels": hbm, "cpu_baseline": cpu,
+                "gpu_baseline": gpu_base, "parity_multi_gpu": parity_multi,
                 "other_kernels_seconds": prof.other_summary}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -574,6 +750,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-b512", action="store_true", help="reference arm: skip the one-off B=512 CPU sample")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-on-CUDA yardstick")
+    ap.add_argument("--obs-store", default="u8", choices=["u8", "f32"],
+                    help="rollout observation store: uint8 bytes (lossless, observations are uint8/255) or the reference's fp32")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

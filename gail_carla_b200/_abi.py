@@ -105,6 +105,10 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32):
         return None
     if not t.is_cuda:
         raise RuntimeError("gail_carla_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if t.get_device() != torch.cuda.current_device():
+        # kernels, tensor maps and the stream handle are issued on the CURRENT device: refuse pointers of another one
+        raise RuntimeError(f"tensor lives on cuda:{t.get_device()} but the current device is cuda:{torch.cuda.current_device()}: "
+                           "call torch.cuda.set_device(...) (or use `with torch.cuda.device(...)`) first")
     if t.dtype != dtype:
         raise TypeError(f"expected {dtype}, got {t.dtype}")
     return t.data_ptr()

@@ -55,6 +55,39 @@ __global__ void __launch_bounds__(384) gather_obs_s2d_kernel(const SrcT* __restr
   }
 }
 
+// uint8 source (byte store of the rollout, expert table): one CTA per (sample, 8 s2d rows).  The two IEEE divisions per
+// element of ToTensor + Normalize ((u/255 - mean)/std, tools/model.py:154-161) cost more issue slots than the copy itself,
+// so they are taken once per CTA into a 3 x 256 look-up table (bit-identical by construction: the same expression on
+// the same 256 inputs); the 48 source rows are staged as bytes with 16-byte loads and every thread then writes whole
+// (c0,c1,c2,1) float4 pixels of the space-to-depth image - 2.4 KB in, 36.9 KB out per CTA, fully coalesced.
+constexpr int kG8Rows = 8;
+__global__ void __launch_bounds__(256) gather_obs_u8_s2d_kernel(const unsigned char* __restrict__ src,
+                                                                const long long* __restrict__ idx, float* __restrict__ out) {
+  __shared__ float lut[kObsC][256];
+  __shared__ __align__(16) unsigned char tile[kObsC][2 * kG8Rows][kObsW + 16];
+  const int b = blockIdx.y, Y0 = blockIdx.x * kG8Rows;
+  const long row = idx ? idx[b] : b;
+  const unsigned char* img = src + row * (long)(kObsC * kObsH * kObsW);
+  constexpr int kRowV = kObsW / 16;  // 16-byte groups per image row
+  for (int i = threadIdx.x; i < kObsC * 2 * kG8Rows * kRowV; i += blockDim.x) {
+    const int v = i % kRowV, r = (i / kRowV) % (2 * kG8Rows), c = i / (kRowV * 2 * kG8Rows);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(img + ((long)c * kObsH + 2 * Y0 + r) * kObsW) + v);
+    *reinterpret_cast<uint4*>(&tile[c][r][16 * v]) = q;
+  }
+  for (int i = threadIdx.x; i < kObsC * 256; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    lut[c][u] = ((float)u / 255.f - c_mean[c]) / c_std[c];
+  }
+  __syncthreads();
+  float4* o = reinterpret_cast<float4*>(out + ((long)b * kS2dH + Y0) * (kS2dW * kS2dC));
+  for (int i = threadIdx.x; i < kG8Rows * kS2dW * 4; i += blockDim.x) {  // one float4 = (c0,c1,c2,1) of one (Y,X,dy,dx)
+    const int yy = i / (kS2dW * 4), j = i % (kS2dW * 4);
+    const int X = j >> 2, dy = (j >> 1) & 1, dx = j & 1;
+    const int x = 2 * X + dx, r = 2 * yy + dy;
+    o[i] = make_float4(lut[0][tile[0][r][x]], lut[1][tile[1][r][x]], lut[2][tile[2][r][x]], 1.f);
+  }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ out,
                                    int B, int width, long ldo) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -432,9 +465,9 @@ int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B,
 int gc_gather_obs_u8_s2d(const unsigned char* src, const long long* idx, float* out, int B, void* stream) {
   GC_REQUIRE(src && out && B > 0, "gc_gather_obs_u8_s2d: bad arguments");
   GC_REQUIRE(B <= 65535, "gc_gather_obs_u8_s2d: B=%d exceeds grid.y", B);
-  GC_REQUIRE(((uintptr_t)src & 3) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_u8_s2d: src must be 4-byte, out 16-byte aligned");
-  gather_obs_s2d_kernel<unsigned char><<<dim3(kS2dH / kGatherRows, B), 384, 0, (cudaStream_t)stream>>>(src, idx, out);
-  return gc::launch_status("gather_obs_s2d_kernel<u8>");
+  GC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_u8_s2d: pointers must be 16-byte aligned");
+  gather_obs_u8_s2d_kernel<<<dim3(kS2dH / kG8Rows, B), 256, 0, (cudaStream_t)stream>>>(src, idx, out);
+  return gc::launch_status("gather_obs_u8_s2d_kernel");
 }
 
 int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream) {

@@ -189,6 +189,15 @@ def shared_workspace(device, rows: int, with_input_grad: bool) -> Workspace:
     return ws
 
 
+def release_workspaces() -> None:
+    """Free every shared workspace (they are re-created on demand)."""
+    for ws in _SHARED.values():
+        ws.release()
+    _SHARED.clear()
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
 def _splits_for(m_tiles: int, n_tiles: int, k_iters: int, cap: int = 8) -> int:
     tiles = max(1, m_tiles * n_tiles)
     s = max(1, min(cap, (2 * 148) // tiles))

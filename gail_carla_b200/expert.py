@@ -143,11 +143,15 @@ class DeviceExpertLoader:
 
 def expert_rows(batch, device):
     """(obs rows, metrics rows, action rows, idx or None, batch size) of an expert batch in either form: a
-    ``DeviceBatch`` (tables + indices, nothing copied) or the reference's ``(obs, metrics, action)`` tensors."""
+    ``DeviceBatch`` (tables + indices, nothing copied) or the reference's ``(obs, metrics, action)`` tensors (obs fp32, or
+    uint8 bytes standing for b/255 - what ``ExpertDataset.obs_u8`` holds)."""
     if isinstance(batch, DeviceBatch):
         return batch.obs_table, batch.metrics_table, batch.actions_table, batch.idx, batch.batch_rows
     obs, met, act = batch
-    obs = obs.to(device, torch.float32, non_blocking=True).contiguous()
+    if obs.dtype == torch.uint8:      # bytes standing for b/255 (ToTensor of the PNGs): gathered by gc_gather_obs_u8_s2d
+        obs = obs.to(device, non_blocking=True).contiguous()
+    else:
+        obs = obs.to(device, torch.float32, non_blocking=True).contiguous()
     met = met.to(device, torch.float32, non_blocking=True).contiguous()
     act = act.to(device, torch.float32, non_blocking=True).contiguous()
     return obs, met, act, None, int(obs.shape[0])

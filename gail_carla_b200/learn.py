@@ -161,6 +161,8 @@ def gail_learning(run_params: dict, envs, env_eval, actor_critic, agent, discrim
                   device, writer=None, model_path: str = "gail_model.pt", verbose: bool = False) -> ScalarLog:
     """The loop of tools/learn.py ``gailLearning_mujoco_origin``; returns the scalar log."""
     log = ScalarLog(writer)
+    if torch.device(device).type == "cuda" and torch.device(device).index is not None:
+        torch.cuda.set_device(torch.device(device))     # kernels and streams are issued on the current device
     nenv = len(run_params["envs_params"])
     nbatch = int(math.floor(run_params["num_steps"] / nenv))
     nupdates = int(math.floor(run_params["num_env_steps"] / run_params["num_steps"]))

@@ -22,8 +22,28 @@ from . import _abi as A
 from .engine import FlatParams
 
 
+_FORCE_SINGLE = False
+
+
 def world_size() -> int:
+    if _FORCE_SINGLE:
+        return 1
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class single_process:
+    """Context manager: run the update classes as a stand-alone process even though a process group is initialised
+    (used to replay a sharded run on the concatenated envs inside one rank for the multi-GPU parity check)."""
+
+    def __enter__(self):
+        global _FORCE_SINGLE
+        self._old, _FORCE_SINGLE = _FORCE_SINGLE, True
+        return self
+
+    def __exit__(self, *exc):
+        global _FORCE_SINGLE
+        _FORCE_SINGLE = self._old
+        return False
 
 
 class GradReducer:

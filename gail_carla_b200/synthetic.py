@@ -81,12 +81,16 @@ class SyntheticExpertLoader:
     when ``pin=True``) and replayed in order on every pass.
     """
 
-    def __init__(self, n_batches: int, batch_size: int, seed: int = 2, pin: bool = False):
+    def __init__(self, n_batches: int, batch_size: int, seed: int = 2, pin: bool = False, obs_u8: bool = False):
+        """obs_u8: yield the observations as the uint8 bytes they are made of (b stands for b/255, what the PNGs of
+        algo/wdgail.py:222-227 hold) instead of fp32 - 4x fewer bytes to keep on the host and to upload."""
         self.batch_size = batch_size
         g = _gen(seed)
         self._batches = []
         for _ in range(n_batches):
             b = (synth_obs(batch_size, g), synth_metrics(batch_size, g), synth_actions(batch_size, g, 0.1))
+            if obs_u8:
+                b = (torch.round(b[0] * 255.0).to(torch.uint8),) + b[1:]
             if pin:
                 b = tuple(t.pin_memory() for t in b)
             self._batches.append(b)

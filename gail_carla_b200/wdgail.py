@@ -161,6 +161,7 @@ class Discriminator(nn.Module):
         self.optimizer = FusedClipAdam(lambda: self.engine.flat, self.parameters(), lr, eps, betas, max_grad_norm)
         self.returns = None
         self.ret_rms = RunningMeanStd(shape=())     # constructed and never used, as in algo/wdgail.py:37-38
+        self.exact_sharding = False                 # multi-GPU exact mode, see PPO.exact_sharding
 
     @property
     def engine(self) -> CriticEngine:
@@ -344,7 +345,7 @@ class Discriminator(nn.Module):
         # exact multi-GPU mode (see PPO.exact_sharding): `expert_loader` yields the same GLOBAL batches of B rows on every
         # rank, the policy minibatch is a global one, and this rank processes the positions whose env it owns - expert row
         # i, policy row i and alpha[i] stay paired exactly as algo/wdgail.py:66-80 pairs them
-        exact = bool(getattr(self, "exact_sharding", False)) and world > 1
+        exact = bool(self.exact_sharding) and world > 1
         if exact and rollouts.shard != (rank, world):
             raise RuntimeError("exact_sharding needs rollouts.set_shard(rank, world) on every rank")
         self.optimizer.grad_scale = 1.0 if exact else None
@@ -410,22 +411,28 @@ class Discriminator(nn.Module):
         dev = self._dev()
         B = expert_loader.batch_size
         world = world_size()
+        exact = bool(self.exact_sharding) and world > 1
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
         acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
+        if exact:     # same global permutation / expert batches on every rank, each evaluates the positions it owns
+            pairs = ((_rows_of(e, pos), idx) for e, (pos, idx) in zip(expert_loader, rollouts.sharded_minibatches(B, batch_size)))
+        else:
+            pairs = zip(expert_loader, rollouts.minibatch_indices(B, batch_size))
         with torch.no_grad():
-            for expert_batch, idx in zip(expert_loader, rollouts.minibatch_indices(B, batch_size)):
-                eng.workspace(3 * B)
-                e_obs, e_met, e_act, e_idx, _ = expert_rows(expert_batch, dev)
-                eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
-                eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
-                eng.tail_features(B, 0); eng.tail_features(B, B)
-                d = eng.forward(2 * B)
-                A.disc_loss_seed(d, eng.ws.buf("dd", eng.ws.rows), acc, B)     # only the tanh sums are used here
-                n += B
-        if world > 1:           # every rank evaluated its own shard: report the mean over all of them
+            for expert_batch, idx in pairs:
+                Bl = int(idx.shape[0])
+                if Bl:
+                    eng.workspace(3 * Bl)
+                    e_obs, e_met, e_act, e_idx, _ = expert_rows(expert_batch, dev)
+                    eng.load_inputs(e_obs, e_met, e_act, e_idx, Bl, 0)
+                    eng.load_inputs(obs_rows, met_rows, act_rows, idx, Bl, Bl)
+                    eng.tail_features(Bl, 0); eng.tail_features(Bl, Bl)
+                    d = eng.forward(2 * Bl)
+                    A.disc_loss_seed(d, eng.ws.buf("dd", eng.ws.rows), acc, Bl)     # only the tanh sums are used here
+                n += B if exact else Bl * world
+        if world > 1:           # every rank evaluated its own rows: report the mean over all of them
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-            n *= world
         _, _, s_te, s_tp = acc[:4].cpu().tolist()
         if n == 0:
             return 0, 0, 0

@@ -77,8 +77,8 @@ def init_disc_params(hidden_dim: int = 100) -> Params:
 # --------------------------------------------------------------------------- #
 def obs_features(p: Params, prefix: str, obs: torch.Tensor) -> torch.Tensor:
     """tools/model.py:157-164: per-channel normalise, 4x conv(k4,s2)+LeakyReLU, flatten (NCHW order)."""
-    mean = torch.tensor(NORM_MEAN, dtype=obs.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(NORM_STD, dtype=obs.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(NORM_MEAN, dtype=obs.dtype, device=obs.device).view(1, 3, 1, 1)
+    std = torch.tensor(NORM_STD, dtype=obs.dtype, device=obs.device).view(1, 3, 1, 1)
     x = (obs - mean) / std
     for i in range(4):
         x = F.conv2d(x, p[f"{prefix}main.{2 * i}.weight"], p[f"{prefix}main.{2 * i}.bias"], stride=2)
@@ -98,8 +98,8 @@ def metrics_features(emb: torch.Tensor, metrics: torch.Tensor) -> torch.Tensor:
     cols = [1000 * torch.from_numpy(x).float(), 1000 * torch.from_numpy(y).float(),
             1000 * torch.from_numpy(r).float(), 0.3 * torch.from_numpy(th).float(),
             0.1 * torch.from_numpy(m[:, 2]).float()]
-    head = torch.stack(cols, dim=1)
-    idx = torch.from_numpy(m[:, 3]).long()
+    head = torch.stack(cols, dim=1).to(metrics.device)          # tools/model.py:207 .to(metrics.device)
+    idx = torch.from_numpy(m[:, 3]).long().to(metrics.device)   # tools/model.py:204
     return torch.cat([head, emb[idx]], dim=1)
 
 
@@ -116,7 +116,7 @@ def policy_base(p: Params, obs, metrics, activation: bool, logstd: Sequence[floa
     mu = out[:, 1:]
     if activation:  # tools/model.py:80-82
         mu = torch.stack([torch.tanh(mu[:, 0]), torch.sigmoid(mu[:, 1])], dim=1)
-    ls = torch.tensor(list(logstd), dtype=mu.dtype).view(1, 2).expand_as(mu)
+    ls = torch.tensor(list(logstd), dtype=mu.dtype, device=mu.device).view(1, 2).expand_as(mu)
     return value, mu, ls
 
 
@@ -242,7 +242,8 @@ def _leaf(params: Params) -> Params:
 # --------------------------------------------------------------------------- #
 def ppo_update(params: Params, adam: AdamState, ro: dict, *, clip_param: float, ppo_epoch: int,
                mini_batch_size: int, value_loss_coef: float, max_grad_norm: float,
-               activation=True, logstd=(-1.4, -3.2), expert_loader=None, bc_gamma=None, decay=None):
+               activation=True, logstd=(-1.4, -3.2), expert_loader=None, bc_gamma=None, decay=None,
+               use_clipped_value_loss=True):
     """algo/ppo.py:45-141.  ``ro`` holds the RolloutStorage tensors by attribute name.
 
     Updates ``params`` in place; returns (8-tuple like the reference, new bc_gamma).
@@ -262,6 +263,8 @@ def ppo_update(params: Params, adam: AdamState, ro: dict, *, clip_param: float, 
             leaf = _leaf(params)
             values, logp, ent, s_std, t_std = evaluate_actions(leaf, obs[idx], met[idx], act[idx], activation, logstd)
             value_loss, action_loss = ppo_losses(values, logp, olp[idx], adv[idx], vold[idx], ret[idx], clip_param)
+            if not use_clipped_value_loss:  # algo/ppo.py:112-113
+                value_loss = 0.5 * (ret[idx] - values).pow(2).mean()
             acc["ga"] += action_loss.item()
             if expert_loader:  # algo/ppo.py:88-102: first batch of a fresh iterator
                 for e_obs, e_met, e_act in expert_loader:
@@ -294,6 +297,7 @@ def grad_penalty(leaf: Params, e, pbatch, alpha: torch.Tensor, lambda_: float = 
     Note metrics are mixed *before* ProcessMetrics, so the road option is int(alpha*c_e+(1-alpha)*c_p).
     """
     B = e[0].shape[0]
+    alpha = alpha.to(e[0].device)           # algo/wdgail.py:68 (.to(expert_state.device))
     a2 = alpha.view(B, 1)
     x = (alpha * e[0] + (1 - alpha) * pbatch[0]).detach().requires_grad_(True)
     m = a2 * e[1] + (1 - a2) * pbatch[1]

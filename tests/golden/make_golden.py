@@ -75,14 +75,14 @@ def gae_case(T, N, seed):
                 returns=ro.returns.numpy(), adv_norm=adv_n.numpy(), gamma=HP["gamma"], gae_lambda=HP["gae_lambda"])
 
 
-def update_case(T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed=1):
+def update_case(T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed=1, clipped=True):
     t0 = time.time()
     sp = NS(shape=(4,)); asp = NS(shape=(2,))
     torch.manual_seed(seed); np.random.seed(seed)
     pol = RefPolicy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False)
     agent = RefPPO(pol, HP["clip_param"], ppo_epoch, B_ppo, HP["value_loss_coef"], "cpu", lr=HP["lr"], eps=HP["eps"],
                    betas=HP["betas"], max_grad_norm=HP["max_grad_norm"], gamma=0.3 if bc else None,
-                   decay=0.9 if bc else None, act_space=asp)
+                   decay=0.9 if bc else None, act_space=asp, use_clipped_value_loss=clipped)
     disc = RefDisc(synthetic.OBS_SHAPE, sp, asp, 100, "cpu", HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
                    HP["gail_max_grad_norm"])
     # oracle twins built from the same seed must be identical to the reference modules
@@ -143,7 +143,7 @@ def update_case(T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed=1
                        mini_batch_size=B_ppo, value_loss_coef=HP["value_loss_coef"],
                        max_grad_norm=HP["max_grad_norm"], logstd=HP["logstd"],
                        expert_loader=loader if bc else None, bc_gamma=0.3 if bc else None,
-                       decay=0.9 if bc else None)
+                       decay=0.9 if bc else None, use_clipped_value_loss=clipped)
 
     def close(a, b, what, rtol=2e-4, atol=2e-5):
         a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
@@ -163,7 +163,7 @@ def update_case(T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed=1
         close(v, out["pol|" + k], "pol " + k[-40:], rtol=1e-3, atol=3e-4 if "sum" not in k else 1e-1)
     for k, v in param_digest(o_disc).items():
         close(v, out["disc|" + k], "disc " + k[-40:], rtol=1e-3, atol=6e-4 if "sum" not in k else 1e-1)
-    out["config"] = np.array([T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, int(bc), seed])
+    out["config"] = np.array([T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, int(bc), seed, int(clipped)])
     print(f"   case done in {time.time() - t0:.1f}s")
     return out
 
@@ -184,6 +184,14 @@ def rms_case():
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    if "--only-new" in sys.argv:      # round 2 additions (the older files are reproducible with the default run)
+        print("update unclipped (T=6,N=2,B=6, use_clipped_value_loss=False)")
+        np.savez_compressed(os.path.join(HERE, "update_unclipped.npz"),
+                            **update_case(T=6, N=2, B_ppo=6, B_gail=6, ppo_epoch=1, gail_epoch=1, n_expert=2, bc=False, clipped=False))
+        print("update mid (T=64,N=8,B=256: 2 minibatches per epoch, BC mix on, multi-tile / split-K shapes)")
+        np.savez_compressed(os.path.join(HERE, "update_mid.npz"),
+                            **update_case(T=64, N=8, B_ppo=256, B_gail=256, ppo_epoch=1, gail_epoch=1, n_expert=2, bc=True))
+        return
     print("gae cases")
     np.savez_compressed(os.path.join(HERE, "gae_64x4.npz"), **gae_case(64, 4, 5))
     np.savez_compressed(os.path.join(HERE, "gae_2048x16.npz"), **gae_case(2048, 16, 6))

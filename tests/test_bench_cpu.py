@@ -9,8 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_the_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--no-b512"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -19,7 +19,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("configs[3]")
+    # the line names what actually ran (the bounded CPU sample) and the workload it stands for
+    assert d["config"]["workload"].startswith("configs[0]") and d["config"]["sample_of"].startswith("configs[3]")
+    assert (d["config"]["T"], d["config"]["N"], d["config"]["B_ppo"]) == (128, 1, 128)
 
 
 def test_reference_arm_other_ranks_exit_quietly():

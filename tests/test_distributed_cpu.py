@@ -67,3 +67,79 @@ def test_two_rank_update_keeps_replicas_identical():
         assert ok_stats, f"rank {rank}: all-reduced advantage statistics differ from the concatenated shards"
         assert same, f"rank {rank}: parameters diverged from rank 0 after the all-reduced update"
         assert norm > 0
+
+
+def _exact_worker(rank, world, port, q):
+    """Exact-mode sharding: the 2-rank run on env shards must reproduce the UNMODIFIED reference's single-process
+    result on the concatenated envs (tests/golden/update_tiny2.npz) - same global permutations, same mix-up draws,
+    global-batch gradients before the clip (tools/storage.py:60-66, algo/ppo.py:115-119, algo/wdgail.py:112-145)."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace as NS
+    import numpy as np
+    from gail_carla_b200 import _abi
+    from oracle import abi_emu
+    for name in dir(abi_emu):
+        fn = getattr(abi_emu, name)
+        if callable(fn) and not name.startswith("_") and hasattr(_abi, name) and name not in ("call", "load_library"):
+            setattr(_abi, name, fn)
+    _abi.EMULATED = True
+    import gail_carla_b200 as G
+    from gail_carla_b200 import synthetic
+    from gail_carla_b200.driver import update_iteration
+    import test_host_cpu as H
+    torch.set_num_threads(2)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "update_tiny2.npz"))
+    T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed = (int(v) for v in z["config"][:9])
+    Nl = N // world
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+    torch.manual_seed(seed)
+    pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, H.HP["logstd"], False)
+    agent = G.PPO(pol, H.HP["clip_param"], ppo_epoch, B_ppo // world, H.HP["value_loss_coef"], "cpu", lr=H.HP["lr"], eps=H.HP["eps"],
+                  betas=H.HP["betas"], max_grad_norm=H.HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+    disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, "cpu", H.HP["gail_lr"], H.HP["gail_eps"], H.HP["gail_betas"],
+                           H.HP["gail_max_grad_norm"])
+    agent.exact_sharding = disc.exact_sharding = True
+    full = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device="cpu")
+    synthetic.fill_rollout(full, seed=seed + 10)
+    ro = G.RolloutStorage(T, Nl, synthetic.OBS_SHAPE, (4,), (2,), device="cpu")
+    for k in ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks", "gail_rewards", "rewards"):
+        getattr(ro, k).copy_(getattr(full, k)[:, rank * Nl:(rank + 1) * Nl])
+    ro.set_shard(rank, world)
+    loader = synthetic.SyntheticExpertLoader(n_expert, B_gail, seed=seed + 20)     # the same global batches on every rank
+    torch.manual_seed(seed + 100)
+    d_out, p_out, cl0, cl1 = update_iteration(pol, agent, disc, ro, loader, gamma=H.HP["gamma"], gae_lambda=H.HP["gae_lambda"],
+                                              gail_epoch=gail_epoch, bcgail=False, diagnostics=True)
+    err = None
+    try:
+        def close(a, b, what, rtol=2e-3, atol=2e-4):
+            a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+            assert np.allclose(a, b, rtol=rtol, atol=atol, equal_nan=True), f"{what}: {a} vs {b}"
+        close(cl0, z["compute_loss_before"], "compute_loss before")
+        close(d_out, z["disc_update"], "Discriminator.update tuples")
+        close(cl1, z["compute_loss_after"], "compute_loss after")
+        close(ro.gail_rewards.numpy(), z["gail_rewards"][:, rank * Nl:(rank + 1) * Nl], "gail_rewards shard")
+        close(ro.returns.numpy(), z["returns"][:, rank * Nl:(rank + 1) * Nl], "returns shard")
+        close([np.nan if x is None else x for x in p_out], z["ppo_update"], "PPO.update tuple")
+        H.digest_check(disc.state_dict(), z, "disc", H.HP["gail_lr"], gail_epoch * min(n_expert, T * N // B_gail))
+        H.digest_check(pol.state_dict(), z, "pol", H.HP["lr"], ppo_epoch * (T * N // B_ppo))
+    except AssertionError as ex:
+        err = str(ex)[:500]
+    q.put((rank, err))
+    dist.destroy_process_group()
+
+
+def test_two_rank_exact_sharding_matches_single_process_reference():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_exact_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err is None, f"rank {rank}: {err}"

@@ -34,29 +34,33 @@ def digest_check(sd, z, prefix, lr, steps, mean_frac=0.05):
         assert d.mean() <= mean_frac * lr, f"{prefix} {k}: mean abs diff {d.mean():.3g} > {mean_frac * lr:.3g}"
 
 
-def run_update_case(name, device):
+def run_update_case(name, device, obs_dtype=torch.float32, expert_u8=False):
+    """obs_dtype=torch.uint8: the rollout lives in the byte store (storage.ByteObs); expert_u8: the expert loader yields
+    uint8 observation batches.  The synthetic observations are on the uint8/255 grid, so both must reproduce the fp32
+    results bit for bit up to the kernels' own rounding - the same goldens apply."""
     import gail_carla_b200 as G
     from gail_carla_b200 import synthetic
     from gail_carla_b200.driver import update_iteration
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed = (int(v) for v in z["config"])
+    T, N, B_ppo, B_gail, ppo_epoch, gail_epoch, n_expert, bc, seed = (int(v) for v in z["config"][:9])
+    clipped = bool(z["config"][9]) if len(z["config"]) > 9 else True
     sp, asp = NS(shape=(4,)), NS(shape=(2,))
     torch.manual_seed(seed); np.random.seed(seed)
     pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False)
     agent = G.PPO(pol, HP["clip_param"], ppo_epoch, B_ppo, HP["value_loss_coef"], device, lr=HP["lr"], eps=HP["eps"],
                   betas=HP["betas"], max_grad_norm=HP["max_grad_norm"], gamma=0.3 if bc else None,
-                  decay=0.9 if bc else None, act_space=asp)
+                  decay=0.9 if bc else None, act_space=asp, use_clipped_value_loss=clipped)
     disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, device, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
                            HP["gail_max_grad_norm"])
     pol.to(device); disc.to(device)
     ro = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device="cpu")
     synthetic.fill_rollout(ro, seed=seed + 10)
-    if device != "cpu":
-        ro_dev = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=device)
+    if device != "cpu" or obs_dtype != torch.float32:
+        ro_dev = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device=device, obs_dtype=obs_dtype)
         for k in ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks", "gail_rewards", "rewards"):
-            getattr(ro_dev, k).copy_(getattr(ro, k))
+            getattr(ro_dev, k).copy_(getattr(ro, k))      # fp32 -> ByteObs goes through the exactness-checked quantiser
         ro = ro_dev
-    loader = synthetic.SyntheticExpertLoader(n_expert, B_gail, seed=seed + 20)
+    loader = synthetic.SyntheticExpertLoader(n_expert, B_gail, seed=seed + 20, obs_u8=expert_u8)
     torch.manual_seed(seed + 100)
     d_out, p_out, cl0, cl1 = update_iteration(pol, agent, disc, ro, loader, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
                                               gail_epoch=gail_epoch, bcgail=bool(bc), diagnostics=True)
@@ -84,9 +88,15 @@ def check_update_case(z, pol, disc, ro, d_out, p_out, cl0, cl1, tol, mean_frac=0
     close(lp.cpu().numpy(), z["act_logp"], "act logp", rtol=tol * 5, atol=tol * 5)
 
 
-@pytest.mark.parametrize("name", ["update_tiny", "update_tiny2"])
+@pytest.mark.parametrize("name", ["update_tiny", "update_tiny2", "update_unclipped"])
 def test_update_iteration_matches_reference_cpu(emulated_abi, name):
     out = run_update_case(name, "cpu")
+    check_update_case(*out, tol=2e-3)
+
+
+def test_update_iteration_uint8_store_matches_reference_cpu(emulated_abi):
+    """Byte store for the rollout + uint8 expert batches: same goldens, same tolerance (lossless by construction)."""
+    out = run_update_case("update_tiny", "cpu", obs_dtype=torch.uint8, expert_u8=True)
     check_update_case(*out, tol=2e-3)
 
 

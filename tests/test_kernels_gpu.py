@@ -264,3 +264,18 @@ def test_weight_layouts_roundtrip_and_adam():
         res[tag] = (P, M, V, ss)
     for a_, b_, nm in zip(res["gpu"], res["ref"], "PMVs"):
         close(a_, b_, 1e-5, 1e-7, "adam " + nm)
+    # round-2 arguments: gradient scale (1/world after a NCCL sum), zero_grad folded into the Adam pass, hyper-parameters
+    # read from device memory (CUDA-graph replay)
+    res = {}
+    for tag, mod, dev in (("ref", E, "cpu"), ("gpu", A, DEV)):
+        P, G = p.clone().to(dev), (gr * 4).clone().to(dev); M = torch.zeros(n, device=dev); V = torch.zeros(n, device=dev)
+        ss = torch.zeros(1, dtype=torch.float64, device=dev)
+        mod.grad_sumsq(G, n, ss, 0.25)
+        hyper = torch.tensor([1e-3, 1 - 0.9, 1 - 0.99], device=dev)
+        mod.clip_adam(P, G, M, V, n, ss, 0.5, 123.0, 0.9, 0.99, 1e-8, 0.5, 0.5, 0.25, True, hyper)
+        res[tag] = (P, M, V, ss, G)
+    for a_, b_, nm in zip(res["gpu"], res["ref"], "PMVsG"):
+        close(a_, b_, 1e-5, 1e-7, "adam (scaled, zeroing, device hyper) " + nm)
+    assert float(res["gpu"][4].abs().max()) == 0.0
+    ss1 = torch.zeros(1, dtype=torch.float64, device=DEV); A.grad_sumsq(gr.to(DEV), n, ss1)
+    close(res["gpu"][3], ss1, 1e-6, 0, "scaled sumsq == sumsq of the scaled gradient")

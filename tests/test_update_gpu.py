@@ -15,9 +15,18 @@ import test_host_cpu as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,tol", [("update_tiny", 2e-2), ("update_tiny2", 5e-2), ("update_c1", 2e-2)])
+@pytest.mark.parametrize("name,tol", [("update_tiny", 2e-2), ("update_tiny2", 5e-2), ("update_c1", 2e-2),
+                                      ("update_unclipped", 2e-2), ("update_mid", 2e-2)])
 def test_update_iteration_matches_reference_gpu(name, tol):
     out = H.run_update_case(name, "cuda")
+    H.check_update_case(*out, tol=tol, mean_frac=0.5)
+
+
+@pytest.mark.parametrize("name,tol", [("update_tiny", 2e-2), ("update_mid", 2e-2)])
+def test_update_iteration_uint8_store_matches_reference_gpu(name, tol):
+    """Rollout in the byte store + uint8 expert batches (lossless: observations are uint8/255 by construction)."""
+    import torch
+    out = H.run_update_case(name, "cuda", obs_dtype=torch.uint8, expert_u8=True)
     H.check_update_case(*out, tol=tol, mean_frac=0.5)
 
 
