@@ -460,6 +460,9 @@ def run_b200(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     A.load_library()
+    if args.no_graphs:
+        from gail_carla_b200 import graphs as _graphs
+        _graphs.ENABLED = False
     parity_multi = multi_gpu_parity(dev, rank, world) if world > 1 else None
     prof = Profiler(A)
     pk = peaks()
@@ -510,9 +513,9 @@ def run_b200(args):
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = prof.launches
+    launches0 = A.LAUNCHES          # C-ABI kernel launches, graph replays included (gail_carla_b200/graphs.py)
     dt = timed(step, args.steps)
-    launches = prof.launches - launches0
+    launches = A.LAUNCHES - launches0
     clocks = sampler.stop() if sampler else None
     env_steps = T * N_total
     value = env_steps * args.steps / dt
@@ -661,9 +664,13 @@ def run_b200(args):
     d2h = result_host.numel() * 4 + 8 * 15
 
     # ---- instrumented step: per-contraction CUDA events -> tensor-pipe roofline of the dominant kernel
+    from gail_carla_b200 import graphs
+    graphs_were = graphs.ENABLED
+    graphs.ENABLED = False            # per-kernel events need eager launches
     prof.armed = True
     step()
     prof.armed = False
+    graphs.ENABLED = graphs_were
     by, tot_f, tot_t = prof.summary()
     step_s = dt / args.steps
     tf32_peak = pk["bf16"] / 2.0
@@ -707,6 +714,7 @@ def run_b200(args):
             del a_, b_
         except Exception as ex:   # pragma: no cover
             roof["tf32_cublas_sustained_tflops"] = None
+    obs_gb = ro.obs.numel() * ro.obs.element_size() / 1e9
     gpu_base = None
     if rank == 0 and world == 1 and not args.no_gpu_baseline:
         # yardstick, measured last with every buffer of the product path released: stock PyTorch on this same GPU
@@ -727,8 +735,9 @@ def run_b200(args):
                 "config": {"workload": c["workload"], "T": T, "N": N_total, "B_ppo": c["B_ppo"], "B_gail": c["B_gail"],
                            "ppo_epoch": c["ppo_epoch"], "gail_epoch": c["gail_epoch"], "envs_per_rank": N,
                            "obs_store": "uint8 bytes (lossless: observations are uint8/255 by construction)" if u8 else "fp32 (reference layout)",
-                           "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % (ro.obs.numel() * ro.obs.element_size() / 1e9),
-                           "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce"},
+                           "l2": "inputs (rollout obs, %.1f GB per rank) are larger than L2" % obs_gb,
+                           "cuda_graphs": not args.no_graphs,
+                           "parallelism": f"env-sharded data parallel x{world}, NCCL grad all-reduce (two buckets, overlapped with the conv backward)"},
                 "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": dt_e2e / args.steps * 1e3, "pinned": pinned,
                         "upload": ("double-buffered" if double else "serial") + ": rollout i+1 is copied from pinned host memory behind "

@@ -118,8 +118,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+LAUNCHES = 0                       # kernels launched through the C ABI (graph replays add their captured count)
+_LAUNCHES_PER_CALL = {"gc_welford_merge": 2, "gc_small_linear_bwd": 2, "gc_conv_wgrad_splits": 0}
+
+
 def call(name: str, *args):
     """Invoke a C-ABI entry point; non-zero status -> RuntimeError(gc_last_error_string())."""
+    global LAUNCHES
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     lib = load_library()
     rc = getattr(lib, name)(*args)
     if rc != 0:

@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         }
         // first channel of this panel (bias index / column guard): sub-tile mode repeats the channel panels per sub-tile
         const int col0 = sub_panels > 0 ? (sub_panels == 1 ? 0 : (q % sub_panels) * 32) : n_tile * p.bn + q * 32;
-        unsigned bits_w = 0u;
+        unsigned bits_w = 0u, bits4[4] = {0u, 0u, 0u, 0u};
         long bits_wi = -1;
         if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) {
           if (bias_smem) {  // bias staged in shared memory: 8 broadcast LDS.128 instead of 32 global loads
@@ -789,23 +789,27 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
           }
           if (epi == EPI_BIAS_LRELU) {
+            if (want_bits) {
+              // LeakyReLU and its derivative bit from ONE comparison per element: predicated multiply for the negative
+              // side, predicated OR of the element's bit for the positive side (bit = output > 0 = pre-activation > 0
+              // for a positive slope).  Four independent accumulators keep the OR chains 8 deep.
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gc::leaky(v[j], slope);
+              for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int i = 8 * c + j;
+                  if (v[i] > 0.f) bits4[c] |= 1u << i;
+                  else v[i] *= slope;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gc::leaky(v[j], slope);
+            }
           }
         }
         if (want_bits) {
-          // bit j = (v[j] > 0), formed without predicates: for the float's bits x as a signed int, x > 0  <=>  the
-          // sign bit of (~x & -x); a funnel shift moves that bit into the word.  Four independent 8-deep chains.
-          unsigned w4[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 7; j >= 0; --j) {
-              const int x = __float_as_int(v[8 * c + j]);
-              w4[c] = __funnelshift_l((unsigned)(~x & -x), w4[c], 1);
-            }
-          }
-          unsigned w = (w4[0] | (w4[1] << 8)) | ((w4[2] << 16) | (w4[3] << 24));
+          unsigned w = (bits4[0] | bits4[1]) | (bits4[2] | bits4[3]);
           if (col0 + 32 > p.n_total) w &= (1u << (p.n_total - col0)) - 1u;   // partial last panel
           bits_w = w;
           if (simple_panels) {
@@ -822,7 +826,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
 #pragma unroll
           for (int qq = 0; qq < 8; ++qq) w = (qq == q) ? mbits[qq] : w;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ((w >> j) & 1u) ? 1.f : slope;
+          for (int j = 0; j < 32; ++j)
+            if (!(w & (1u << j))) v[j] *= slope;   // one bit test + predicated multiply per element
         }
         if (masked) {
           mbar_wait(aux0 + 8 * bi, bph);

@@ -117,18 +117,33 @@ class FusedClipAdam(torch.optim.Optimizer):
     def device_hyper(self, flat: FlatParams) -> torch.Tensor:
         if self._hyper_dev is None:
             dev = flat.flat.device
-            self._hyper_host = torch.zeros(3, pin_memory=dev.type == "cuda")
             self._hyper_dev = torch.zeros(3, device=dev)
         return self._hyper_dev
 
-    def advance(self, flat: FlatParams) -> None:
-        """t += 1 and upload {lr, 1-beta1^t, 1-beta2^t} for the next (graph-replayed) step."""
-        self.t += 1
+    def begin_schedule(self, n_steps: int) -> None:
+        """Upload {lr, 1-beta1^t, 1-beta2^t} for the next `n_steps` optimiser steps in one copy (the learning rate of
+        ``param_groups`` is read here, i.e. once per update like the reference's per-update schedule,
+        tools/learn.py:102-106).  ``advance()`` then selects the row of the step about to run with a device-to-device
+        copy, so neither an eager step nor a graph replay needs a host-side scalar."""
+        flat: FlatParams = self._flat_getter()
+        self._buffers(flat)
         g = self.param_groups[0]
         b1, b2 = g["betas"]
-        hd = self.device_hyper(flat)
-        self._hyper_host[0] = float(g["lr"]); self._hyper_host[1] = 1.0 - b1 ** self.t; self._hyper_host[2] = 1.0 - b2 ** self.t
-        hd.copy_(self._hyper_host, non_blocking=True)
+        dev = flat.flat.device
+        host = torch.empty(max(n_steps, 1), 3, pin_memory=dev.type == "cuda")
+        for i in range(n_steps):
+            t = self.t + i + 1
+            host[i, 0] = float(g["lr"]); host[i, 1] = 1.0 - b1 ** t; host[i, 2] = 1.0 - b2 ** t
+        self._table_host = host                                  # keep the pinned source alive until the next schedule
+        self._table = host.to(dev, non_blocking=True)
+        self._table_i = 0
+
+    def advance(self) -> None:
+        """t += 1; stage this step's scalars where ``step(from_device_hyper=True)`` reads them."""
+        flat: FlatParams = self._flat_getter()
+        self.t += 1
+        self.device_hyper(flat).copy_(self._table[self._table_i], non_blocking=True)
+        self._table_i += 1
 
     @torch.no_grad()
     def step(self, closure=None, *, from_device_hyper: bool = False):

@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 from . import _abi as A
 from .expert import expert_rows
+from .graphs import StepGraph
 from .optim import FusedClipAdam, world_size
 
 
@@ -39,6 +40,8 @@ class PPO():
         # mini_batch_size * world rows, each rank processes the members it owns - bit-for-bit the sample sets, weights
         # and RNG stream of a single process holding all envs (tools/storage.py:60-66, algo/ppo.py:64-119).
         self.exact_sharding = False
+        self._graph = StepGraph("PPO")
+        self._dev_state = None
 
     def update(self, rollouts, expert_dataset=None):
         pol = self.actor_critic
@@ -69,9 +72,40 @@ class PPO():
         Bg = B * world if exact else B            # rows one optimisation step averages over on this rank's scale
         use_bc = bool(expert_dataset)
         w_act = (1.0 - self.gamma) if use_bc else 1.0
-        acc = torch.zeros(4, dtype=torch.float64, device=dev)
         n_updates = 0
         n_bc_rows = 0
+        # per-object device state the (replayable) step reads / writes: loss sums, advantage statistics, row indices
+        if getattr(self, "_dev_state", None) is None or self._dev_state[0].device != dev or self._dev_state[2].numel() != B:
+            self._dev_state = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev),
+                               torch.zeros(B, dtype=torch.int64, device=dev))
+        acc, stats_buf, idx_buf = self._dev_state
+        acc.zero_()
+        stats_buf.copy_(stats)
+        opt = self.optimizer
+        n_sched = self.ppo_epoch * ((T * N * (world if exact else 1)) // Bg)
+        opt.begin_schedule(n_sched)
+        clipped = bool(self.use_clipped_value_loss)
+        clip, vcoef = float(self.clip_param), float(self.value_loss_coef)
+
+        def device_step():
+            """One optimisation step on the rows named by idx_buf: everything is enqueued on the current stream and reads
+            only device-resident state, so it can be captured once and replayed (graphs.StepGraph)."""
+            ws = eng.workspace(B)
+            eng.load_inputs(obs_rows, met_rows, idx_buf, B)
+            a_b = ws.buf("act", ws.rows, 2); vo_b = ws.buf("vold", ws.rows); r_b = ws.buf("ret", ws.rows)
+            lp_b = ws.buf("olp", ws.rows)
+            A.gather_rows(act_rows, idx_buf, a_b, B, 2, 2)
+            A.gather_rows(vp_rows, idx_buf, vo_b, B, 1, 1)
+            A.gather_rows(ret_rows, idx_buf, r_b, B, 1, 1)
+            A.gather_rows(lp_rows, idx_buf, lp_b, B, 1, 1)
+            head = eng.forward(B, training=True)
+            d_head = ws.buf("dhead", ws.rows, 4)
+            A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats_buf, d_head, None, None, acc, B, logstd, act, clip, vcoef, 1.0, 0,
+                       clipped_value=clipped)
+            eng.backward(B, d_head, reducer=opt.reducer)
+            opt.step(from_device_hyper=True)
+            eng.dirty = True
+            eng.sync_params()
 
         def epoch_batches():   # one fresh permutation per epoch (tools/storage.py:60-63)
             if exact:
@@ -80,6 +114,15 @@ class PPO():
 
         for _ in range(self.ppo_epoch):
             for pos, idx in epoch_batches():
+                opt.advance()
+                if not use_bc and not exact:        # the common, fixed-shape step: replayed as one CUDA graph
+                    idx_buf.copy_(idx, non_blocking=True)
+                    ws = eng.workspace(B)
+                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), obs_rows.data_ptr(), ret_rows.data_ptr(), world,
+                           clipped, clip, vcoef, tuple(logstd), act, self.max_grad_norm)
+                    self._graph.run(key, device_step, dev)
+                    n_updates += 1
+                    continue
                 Bl = int(idx.shape[0])             # rows of this step on this rank (== B unless exact sharding)
                 Be = Be_norm = 0
                 e_act = None
@@ -111,17 +154,16 @@ class PPO():
                     head = eng.forward(Bl + Be, training=True)
                     d_head = ws.buf("dhead", ws.rows, 4)
                     if Bl:
-                        A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats, d_head, None, None, acc, Bl, logstd, act,
-                                   float(self.clip_param), float(self.value_loss_coef), float(w_act), 0,
-                                   clipped_value=self.use_clipped_value_loss, norm=Bg if exact else None)
+                        A.ppo_loss(head, a_b, lp_b, vo_b, r_b, None, stats_buf, d_head, None, None, acc, Bl, logstd, act,
+                                   clip, vcoef, float(w_act), 0, clipped_value=clipped, norm=Bg if exact else None)
                     if Be:
                         A.ppo_loss(head[Bl:], e_act, None, None, None, None, None, d_head[Bl:], None, None, acc, Be, logstd, act,
                                    0.0, 0.0, float(self.gamma), 1, norm=Be_norm if exact else None)
-                    eng.backward(Bl + Be, d_head, reducer=self.optimizer.reducer)
+                    eng.backward(Bl + Be, d_head, reducer=opt.reducer)
                 else:            # this rank owns no member of the global minibatch: it contributes a zero gradient
                     eng.flat.begin_backward()
                 n_bc_rows += Be_norm if exact else Be
-                self.optimizer.step()
+                opt.step(from_device_hyper=True)
                 eng.dirty = True
                 eng.sync_params()
                 n_updates += 1

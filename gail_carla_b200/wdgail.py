@@ -25,6 +25,7 @@ from . import engine as E
 from ._abi import LDF, S2D_PER_SAMPLE, EPI_BIAS_LRELU, EPI_MASK, EPI_STORE
 from .model import _Holder, _conv_seq, N_METRIC_FEAT
 from .expert import DeviceBatch, expert_rows
+from .graphs import StepGraph
 from .optim import FusedClipAdam, world_size
 from .running_mean_std import RunningMeanStd
 
@@ -162,6 +163,8 @@ class Discriminator(nn.Module):
         self.returns = None
         self.ret_rms = RunningMeanStd(shape=())     # constructed and never used, as in algo/wdgail.py:37-38
         self.exact_sharding = False                 # multi-GPU exact mode, see PPO.exact_sharding
+        self._graph = StepGraph("critic")
+        self._alpha_buf = self._acc = None
 
     @property
     def engine(self) -> CriticEngine:
@@ -350,7 +353,6 @@ class Discriminator(nn.Module):
             raise RuntimeError("exact_sharding needs rollouts.set_shard(rank, world) on every rank")
         self.optimizer.grad_scale = 1.0 if exact else None
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
-        acc = torch.zeros(8, dtype=torch.float64, device=dev)
         n = 0
         # Mix-up coefficients (algo/wdgail.py:66: torch.rand(B,1,1,1) per batch on the CPU default generator).  All
         # host->device transfers share one DMA queue, so a small per-batch upload on the compute stream would queue
@@ -361,17 +363,35 @@ class Discriminator(nn.Module):
         else:
             pairs = zip(expert_loader, ((None, idx) for idx in rollouts.minibatch_indices(B)))
         alphas = None
-        if hasattr(expert_loader, "__len__") and dev.type == "cuda":
+        n_batches = None
+        if hasattr(expert_loader, "__len__"):
             first = next(pairs, None)          # advances both iterators exactly like the first zip step (draws randperm)
             n_rollout = rollouts.num_steps * rollouts.num_processes * (world if exact else 1)
             n_batches = min(len(expert_loader), n_rollout // B) if first is not None else 0
-            if n_batches:
+            if n_batches and dev.type == "cuda":
                 host = torch.empty(n_batches, B, pin_memory=True)
                 for i in range(n_batches):
                     host[i] = torch.rand(B, 1, 1, 1).view(B)
                 alphas = host.to(dev, non_blocking=True)
             import itertools
             pairs = itertools.chain([first], pairs) if first is not None else iter(())
+        opt = self.optimizer
+        if n_batches:
+            opt.begin_schedule(n_batches)
+        if getattr(self, "_alpha_buf", None) is None or self._alpha_buf.device != dev or self._alpha_buf.numel() != B:
+            self._alpha_buf = torch.zeros(B, device=dev)
+            self._acc = torch.zeros(8, dtype=torch.float64, device=dev)
+        acc, alpha_buf = self._acc, self._alpha_buf
+        acc.zero_()
+
+        def device_step():
+            """Forward + full backward + optimiser step on the 2B rows already gathered into the workspace; reads only
+            device-resident state (alpha_buf, Adam's scalars), so it is captured once and replayed (graphs.StepGraph)."""
+            eng.update_step(B, alpha_buf, acc, reducer=opt.reducer)
+            opt.step(from_device_hyper=True)
+            eng.dirty = True
+            eng.sync_params()
+
         with torch.no_grad():
             for i_batch, (e_batch, (pos, idx), release) in enumerate(self._prefetched(pairs)):
                 e_obs, e_met, e_act, e_idx, e_rows = expert_rows(e_batch, dev)
@@ -382,21 +402,33 @@ class Discriminator(nn.Module):
                     alpha = alphas[i_batch]
                 else:
                     alpha = self._upload_alpha(torch.rand(B, 1, 1, 1).view(B))
-                if exact:
-                    alpha = alpha[pos.to(alpha.device)].contiguous()
+                if n_batches is None or i_batch >= n_batches:
+                    opt.begin_schedule(1)          # loader of unknown length: stage the scalars step by step
+                opt.advance()
+                if not exact:                      # fixed-shape step: inputs gathered eagerly, the rest replayed as a graph
+                    ws = eng.workspace(3 * B)
+                    eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
+                    release()
+                    eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
+                    alpha_buf.copy_(alpha, non_blocking=True)
+                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), world, self.max_grad_norm)
+                    self._graph.run(key, device_step, dev)
+                    n += B * world
+                    continue
+                alpha = alpha[pos.to(alpha.device)].contiguous()
                 if Bl:
                     eng.workspace(3 * Bl)
                     eng.load_inputs(e_obs, e_met, e_act, e_idx, Bl, 0)
                     release()
                     eng.load_inputs(obs_rows, met_rows, act_rows, idx, Bl, Bl)
-                    eng.update_step(Bl, alpha, acc, norm=B if exact else None, reducer=self.optimizer.reducer)
+                    eng.update_step(Bl, alpha, acc, norm=B, reducer=opt.reducer)
                 else:              # this rank owns no member of the global minibatch: zero gradient, still all-reduces
                     release()
                     eng.flat.begin_backward()
-                self.optimizer.step()
+                opt.step(from_device_hyper=True)
                 eng.dirty = True
                 eng.sync_params()
-                n += B if exact else Bl * world
+                n += B
         if world > 1:           # the tuple reports global-batch means (algo/wdgail.py:147)
             dist.all_reduce(acc, op=dist.ReduceOp.SUM)
         s_de, s_dp, s_te, s_tp, s_gp = acc[:5].cpu().tolist()   # single read-back per update

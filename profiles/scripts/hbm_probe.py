@@ -24,6 +24,20 @@ def note(kernel, label, nbytes, launches=2):
     LOG.append(dict(kernel=kernel, label=label, algorithmic_bytes=nbytes, launches=launches))
 
 
+class timed:
+    """CUDA-event time of the enclosed launches (the second, warm one of each pair is what the JSON line reports)."""
+    last_ms = None
+
+    def __enter__(self):
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        self.e1.record(); torch.cuda.synchronize()
+        timed.last_ms = self.e0.elapsed_time(self.e1)
+
+
 def gae(T, N, label):
     r = torch.rand(T, N, 1, device=dev); v = torch.randn(T + 1, N, 1, device=dev); m = (torch.rand(T + 1, N, 1, device=dev) > 0.02).float()
     ret = torch.zeros_like(v)
@@ -60,9 +74,11 @@ def gather(B, rows, label, u8):
     idx = torch.randperm(rows, device=dev)[:B].contiguous()
     out = torch.empty(B, A.S2D_PER_SAMPLE, device=dev)
     for _ in range(2):
-        A.gather_obs_s2d(src, idx, out, B)
+        with timed():
+            A.gather_obs_s2d(src, idx, out, B)
     per = 3 * 192 * 192 * (1 if u8 else 4) + 4 * A.S2D_PER_SAMPLE
-    note("gather_obs_s2d_kernel<%s>" % ("u8" if u8 else "f32"), label, float(per) * B)
+    note("gather_obs_u8_s2d_kernel" if u8 else "gather_obs_s2d_kernel", label, float(per) * B)
+    LOG[-1]["event_ms"] = timed.last_ms; LOG[-1]["event_gbs"] = float(per) * B / timed.last_ms / 1e6
 
 
 def colsum(rows, Cc, label):

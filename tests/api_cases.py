@@ -45,8 +45,9 @@ def evaluate_actions_is_differentiable(device, B, min_cos, max_rel):
     (-(lp_r.mean()) + 0.25 * (v_r * w).sum()).backward()
     ref = {k: v.grad for k, v in leaf.items()}
     GC.compare(got, ref, min_cos, max_rel, "evaluate_actions")
-    assert torch.allclose(value.detach().cpu(), v_r.detach(), rtol=max_rel * 10, atol=max_rel)
-    assert torch.allclose(logp.detach().cpu(), lp_r.detach(), rtol=max_rel * 10, atol=max_rel * 10)
+    fwd_tol = min(max_rel, 5e-3)       # forward values: no mask-flip amplification, TF32 level at most
+    assert torch.allclose(value.detach().cpu(), v_r.detach(), rtol=fwd_tol * 10, atol=fwd_tol)
+    assert torch.allclose(logp.detach().cpu(), lp_r.detach(), rtol=fwd_tol * 10, atol=fwd_tol * 10)
     assert abs(float(ent) - float(ent_r)) < 1e-6
     # accumulation semantics of autograd: a second identical pass doubles p.grad
     value, logp, *_ = pol.evaluate_actions(obs.to(device), met.to(device), act.to(device))
@@ -71,8 +72,10 @@ def forward_gp_returns_first_order_handles(device, B, tol):
     x = obs.clone().requires_grad_(True)
     d = O.disc_forward(params, x, met, act)
     g_ref = torch.autograd.grad(d, x, torch.ones_like(d))[0]
-    assert torch.allclose(out.detach().cpu(), d.detach(), rtol=tol * 10, atol=tol)
+    fwd_tol = min(tol, 5e-3)
+    assert torch.allclose(out.detach().cpu(), d.detach(), rtol=fwd_tol * 10, atol=fwd_tol)
     rel = float((g - g_ref).norm() / g_ref.norm())
+    print(f"forward(gp=True): dD/dx rel-Frobenius {rel:.3e}")
     assert rel <= tol, f"dD/dx rel-Frobenius {rel:.3e}"
     assert torch.allclose(mt.cpu(), O.metrics_features(params["metrics_processor.road_option_embedding.weight"], met), rtol=1e-5, atol=1e-5)
     assert torch.equal(st.detach().cpu(), obs) and torch.equal(at.cpu(), act)

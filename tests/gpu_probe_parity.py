@@ -61,7 +61,35 @@ def report_grads():
               ", ".join(f"{k.split('main.')[1]}={v:.1e}" for k, v in per.items() if "main" in k), flush=True)
 
 
+def report_extra():
+    for B in (64, 200):
+        tf32, fp32 = GC.stock_tf32_policy_grads(B)
+        e = GC.rel_errors(tf32, fp32)
+        k = max(e, key=lambda n: e[n][1])
+        print(f"stock PyTorch TF32 (cuDNN/cuBLAS) vs CPU fp32, policy grads B={B}: worst rel-Fro {e[k][1]:.2e} (cos {e[k][0]:.6f}) at {k}; conv rel: " +
+              ", ".join(f"{n.split('main.')[1]}={v[1]:.1e}" for n, v in e.items() if "main" in n), flush=True)
+        got, ref = GC.policy_grads("cuda", B, 0)
+        m = GC.rel_errors(got, ref)
+        print(f"   this repo vs CPU fp32, same minibatch: " + ", ".join(f"{n.split('main.')[1]}={v[1]:.1e}" for n, v in m.items() if "main" in n)
+              + " | fc: " + ", ".join(f"{v[1]:.1e}" for n, v in m.items() if "main" not in n), flush=True)
+        print(f"   ratio mine/stock per tensor: " + ", ".join(f"{m[n][1] / max(e[n][1], 1e-12):.2f}" for n in m), flush=True)
+    with GC.linearised():
+        for B, Be in ((64, 0), (200, 0)):
+            got, ref = GC.policy_grads("cuda", B, Be)
+            e = GC.rel_errors(got, ref)
+            k = max(e, key=lambda n: e[n][1])
+            print(f"linearised (slope 1) policy grads B={B}: worst rel-Fro {e[k][1]:.2e} (cos {e[k][0]:.7f}) at {k}", flush=True)
+        for B in (32, 100):
+            got, ref, gs, rs = GC.critic_grads("cuda", B)
+            e = GC.rel_errors(got, ref)
+            k = max(e, key=lambda n: e[n][1])
+            print(f"linearised (slope 1) critic grads B={B}: worst rel-Fro {e[k][1]:.2e} (cos {e[k][0]:.7f}) at {k}; gp {gs['gp']:.6f}/{rs['gp']:.6f}", flush=True)
+
+
 if __name__ == "__main__":
+    if "--extra" in sys.argv:
+        report_extra()
+        sys.exit(0)
     report_grads()
     for name in ("update_tiny", "update_tiny2", "update_c1", "update_unclipped", "update_mid"):
         report_case(name)

@@ -104,6 +104,62 @@ def critic_grads(device, B, seed=4):
     return got, ref, got_s, dict(wd=wd.item(), gp=gp.item())
 
 
+class linearised:
+    """LeakyReLU slope 1.0 on both sides (product engines and oracle): the networks become linear maps, no activation
+    mask can flip, and what is left of the deviation is the arithmetic of the contractions themselves."""
+
+    def __enter__(self):
+        from gail_carla_b200 import engine as E
+        from oracle import ref_path as O
+        self.E, self.O, self.old = E, O, (E.SLOPE, O.LRELU)
+        E.SLOPE, O.LRELU = 1.0, 1.0
+        return self
+
+    def __exit__(self, *exc):
+        self.E.SLOPE, self.O.LRELU = self.old
+        return False
+
+
+def stock_tf32_policy_grads(B, seed=3):
+    """The oracle's autograd gradients of the same PPO minibatch computed twice by stock PyTorch: on the CPU in fp32 and
+    on the CUDA device with cuDNN / cuBLAS allowed to use TF32 (the reference's own GPU numerics).  -> (tf32, fp32)."""
+    from oracle import ref_path as O
+    torch.manual_seed(seed)
+    params = O.init_policy_params()
+    obs, met, act = _batch(B, seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    olp = torch.randn(B, generator=g) * 0.5 - 1.0
+    vold = torch.randn(B, generator=g) * 0.3
+    ret = vold + torch.randn(B, generator=g) * 0.5
+    adv = torch.randn(B, generator=g)
+    out = []
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for dev in ("cuda", "cpu"):
+            leaf = O._leaf({k: v.to(dev) for k, v in params.items()})
+            to = lambda t: t.to(dev)
+            values, logp, _, _, _ = O.evaluate_actions(leaf, to(obs), to(met), to(act), True, HP["logstd"])
+            vl, al = O.ppo_losses(values, logp, to(olp).view(-1, 1), to(adv).view(-1, 1), to(vold).view(-1, 1), to(ret).view(-1, 1),
+                                  HP["clip_param"])
+            (vl * HP["value_loss_coef"] + al).backward()
+            out.append({k: v.grad.detach().cpu() for k, v in leaf.items()})
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out[0], out[1]
+
+
+def rel_errors(got, ref):
+    """{name: (cosine, rel-Frobenius)} for the tensors whose reference gradient is non-zero."""
+    out = {}
+    for k, r in ref.items():
+        g = got[k].double().reshape(-1); r = r.double().reshape(-1)
+        if r.norm() == 0:
+            continue
+        out[k] = (float(torch.dot(g, r) / (r.norm() * g.norm() + 1e-300)), float((g - r).norm() / r.norm()))
+    return out
+
+
 def compare(got, ref, min_cos, max_rel, what):
     """Per tensor: cosine >= min_cos and ||got-ref||_F <= max_rel * ||ref||_F (tensors whose reference gradient is exactly
     zero must be zero).  Returns the worst (cos, rel) seen, for the test's printout."""
