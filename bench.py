@@ -688,6 +688,11 @@ def run_b200(args):
             "frac": (tot_f / tot_t / 1e12) / tf32_peak if tot_t else None, "traffic": traffic, "traffic_note": traffic_src,
             "peak_note": f"TF32 dense = 1/2 of the {pk['src']} sustained bf16 peak ({pk['bf16']} TF/s); MEASURED_PEAKS.json has no TF32 entry",
             "share_of_step": tot_t / step_s if step_s else None, "launches": len(prof.records),
+            # mixed roofline: every contraction is bounded by the slower of its tensor time (FLOPs / TF32 peak) and its HBM
+            # time (algorithmic bytes / measured HBM peak; conv layers only - the small-channel layers are HBM-bound);
+            # mixed_frac = sum of those bounds / sum of the measured times
+            "mixed_ideal_seconds": sum(max(v[0] / (tf32_peak * 1e12), v[3] / (pk["hbm"] * 1e9)) for v in by.values()),
+            "mixed_frac": (sum(max(v[0] / (tf32_peak * 1e12), v[3] / (pk["hbm"] * 1e9)) for v in by.values()) / tot_t) if tot_t else None,
             # per contraction: tensor-pipe rate, and for the convolutions the algorithmic HBM rate (the small-channel layers
             # conv1 / conv2 are HBM-bound: ~17 and ~80 FLOP per byte moved)
             "per_op": {k: dict({"tflops": v[0] / v[1] / 1e12, "seconds": v[1], "launches": v[2]},
@@ -748,7 +753,16 @@ def run_b200(args):
                 "other_kernels_seconds": prof.other_summary}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # captured graphs hold NCCL resources: release them before the communicator goes away (see graphs.release_all);
+        # the line is out and every rank is done, so leave without the interpreter's teardown - a hang there (seen once with
+        # live graphs: the NCCL watchdog blocked in an event destroy for minutes) must never cost the run
+        from gail_carla_b200 import graphs as _g
+        torch.cuda.synchronize()
+        dist.barrier()
+        _g.release_all()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

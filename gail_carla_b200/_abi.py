@@ -37,6 +37,7 @@ _SIGNATURES = {
     "gc_welford_merge": [_P, _P, _L, _P, _P],
     "gc_gather_obs_s2d": [_P, _P, _P, _I, _P],
     "gc_gather_obs_u8_s2d": [_P, _P, _P, _I, _P],
+    "gc_gather_pair_mix_u8_s2d": [_P, _P, _P, _P, _P, _P, _I, _P],
     "gc_gather_rows": [_P, _P, _P, _I, _I, _L, _P],
     "gc_mixup": [_P, _P, _P, _P, _I, _L, _P],
     "gc_metrics_features": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
@@ -55,11 +56,11 @@ _SIGNATURES = {
     "gc_grad_sumsq": [_P, _L, _F, _P, _P],
     "gc_clip_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
     "gc_conv_fprop": [_G, _P, _P, _P, _P, _P, _P, _I, _F, _P],
-    "gc_conv_dgrad": [_G, _P, _P, _P, _P, _P, _F, _P],
+    "gc_conv_dgrad": [_G, _P, _P, _P, _P, _P, _F, _P, _I, _P],
     "gc_conv_wgrad_splits": [_G],
     "gc_conv_wgrad": [_G, _P, _P, _P, _I, _P],
     "gc_linear_fwd": [_P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _F, _I, _P],
-    "gc_linear_dgrad": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _F, _P],
+    "gc_linear_dgrad": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _F, _P, _I, _I, _P],
     "gc_linear_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _P],
 }
 ABI_VERSION = 2            # == GC_ABI_VERSION of include/gail_carla_b200.h; bumped whenever a signature changes
@@ -188,6 +189,13 @@ def gather_obs_s2d(src, idx, out, B):
         call("gc_gather_obs_s2d", _ptr(src), _ptr(idx, torch.int64), _ptr(out), B, _stream())
 
 
+def gather_pair_mix(src_e, idx_e, src_p, idx_p, alpha, out, B):
+    """Expert rows, policy rows and their mix-up into out rows [0,B) | [B,2B) | [2B,3B) in one pass (uint8 sources)."""
+    _contig(src_e, idx_e, src_p, idx_p, alpha, out)
+    call("gc_gather_pair_mix_u8_s2d", _ptr(src_e, torch.uint8), _ptr(idx_e, torch.int64), _ptr(src_p, torch.uint8),
+         _ptr(idx_p, torch.int64), _ptr(alpha), _ptr(out), B, _stream())
+
+
 def gather_rows(src, idx, out, B, width, ldo):
     _contig(src, idx)
     call("gc_gather_rows", _ptr(src), _ptr(idx, torch.int64), _ptr(out), B, width, ldo, _stream())
@@ -275,9 +283,11 @@ def conv_fprop(geom: ConvGeom, x, w, bias, y, epilogue, slope=0.2, mask_src=None
          epilogue, slope, _stream())
 
 
-def conv_dgrad(geom: ConvGeom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None):
+def conv_dgrad(geom: ConvGeom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None, dbias_in=None, dbias_samples=0):
+    """dbias_in (needs mask_bits): += per-channel sums of the masked dx over the first `dbias_samples` samples (0: all) - the
+    bias gradient of the layer below, taken from the output tiles instead of a separate column-sum pass."""
     call("gc_conv_dgrad", C.byref(geom), _ptr(dy), _ptr(wd), _ptr(mask_src), _ptr(mask_bits, torch.int32), _ptr(dx), slope,
-         _stream())
+         _ptr(dbias_in), int(dbias_samples), _stream())
 
 
 def conv_wgrad_splits(geom: ConvGeom) -> int:
@@ -295,9 +305,11 @@ def linear_fwd(x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue, slope=0.2, split
     call("gc_linear_fwd", _ptr(x), ldx, _ptr(w), ldw, _ptr(bias), _ptr(y), ldy, M, N, K, epilogue, slope, splits, _stream())
 
 
-def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None):
+def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None, colsum=None, colsum_mod=0,
+                 colsum_rows=0):
+    """colsum (needs mask_bits): colsum[n % colsum_mod] += column sums of the masked dx over the first `colsum_rows` rows."""
     call("gc_linear_dgrad", _ptr(dy), lddy, _ptr(w), ldw, _ptr(mask_src), _ptr(mask_bits, torch.int32), ldm, _ptr(dx), lddx, M, N, K,
-         slope, _stream())
+         slope, _ptr(colsum), int(colsum_mod), int(colsum_rows), _stream())
 
 
 def linear_wgrad(dy, lddy, x, ldx, dw, lddw, M, N, K, splits=1):

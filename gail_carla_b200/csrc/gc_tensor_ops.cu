@@ -88,6 +88,51 @@ __global__ void __launch_bounds__(256) gather_obs_u8_s2d_kernel(const unsigned c
   }
 }
 
+// Critic minibatch in one pass (algo/wdgail.py:66-80,116,121): expert image b, policy image b and their mix-up
+// alpha*e + (1-alpha)*p, all three written as normalised space-to-depth rows [0,B) | [B,2B) | [2B,3B) of `out`.  Same
+// staging as gather_obs_u8_s2d_kernel; the mix is formed from the two normalised pixels in registers (the same two
+// products and one sum gc_mixup computes from the stored images), so the separate mix-up pass - 2 reads and 1 write of the
+// fp32 images - disappears.
+__global__ void __launch_bounds__(256) gather_pair_mix_u8_s2d_kernel(const unsigned char* __restrict__ src_e,
+                                                                     const long long* __restrict__ idx_e,
+                                                                     const unsigned char* __restrict__ src_p,
+                                                                     const long long* __restrict__ idx_p,
+                                                                     const float* __restrict__ alpha, float* __restrict__ out, int B) {
+  __shared__ float lut[kObsC][256];
+  __shared__ __align__(16) unsigned char tile[2][kObsC][2 * kG8Rows][kObsW + 16];
+  const int b = blockIdx.y, Y0 = blockIdx.x * kG8Rows;
+  const long row_e = idx_e ? idx_e[b] : b, row_p = idx_p ? idx_p[b] : b;
+  const unsigned char* img[2] = {src_e + row_e * (long)(kObsC * kObsH * kObsW), src_p + row_p * (long)(kObsC * kObsH * kObsW)};
+  constexpr int kRowV = kObsW / 16;
+  constexpr int kPer = kObsC * 2 * kG8Rows * kRowV;
+  for (int i = threadIdx.x; i < 2 * kPer; i += blockDim.x) {
+    const int which = i / kPer, k = i % kPer;
+    const int v = k % kRowV, r = (k / kRowV) % (2 * kG8Rows), c = k / (kRowV * 2 * kG8Rows);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(img[which] + ((long)c * kObsH + 2 * Y0 + r) * kObsW) + v);
+    *reinterpret_cast<uint4*>(&tile[which][c][r][16 * v]) = q;
+  }
+  for (int i = threadIdx.x; i < kObsC * 256; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    lut[c][u] = ((float)u / 255.f - c_mean[c]) / c_std[c];
+  }
+  __syncthreads();
+  const float a = alpha[b], na = 1.f - a;
+  const long per_row = kS2dW * kS2dC, per_img = (long)kS2dH * per_row;
+  float4* oe = reinterpret_cast<float4*>(out + (long)b * per_img + Y0 * per_row);
+  float4* op = reinterpret_cast<float4*>(out + ((long)B + b) * per_img + Y0 * per_row);
+  float4* om = reinterpret_cast<float4*>(out + (2L * B + b) * per_img + Y0 * per_row);
+  for (int i = threadIdx.x; i < kG8Rows * kS2dW * 4; i += blockDim.x) {
+    const int yy = i / (kS2dW * 4), j = i % (kS2dW * 4);
+    const int X = j >> 2, dy = (j >> 1) & 1, dx = j & 1;
+    const int x = 2 * X + dx, r = 2 * yy + dy;
+    const float e0 = lut[0][tile[0][0][r][x]], e1 = lut[1][tile[0][1][r][x]], e2 = lut[2][tile[0][2][r][x]];
+    const float p0 = lut[0][tile[1][0][r][x]], p1 = lut[1][tile[1][1][r][x]], p2 = lut[2][tile[1][2][r][x]];
+    oe[i] = make_float4(e0, e1, e2, 1.f);
+    op[i] = make_float4(p0, p1, p2, 1.f);
+    om[i] = make_float4(a * e0 + na * p0, a * e1 + na * p1, a * e2 + na * p2, a * 1.f + na * 1.f);
+  }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float* __restrict__ out,
                                    int B, int width, long ldo) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -337,31 +382,45 @@ __global__ void prep_conv1_kernel(const float* __restrict__ w, float* __restrict
   wf[i] = v;
   if (wd) wd[((q * 2 + ky2) * 2 + px) * 32 + n] = v;
 }
-__global__ void unprep_conv_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw, int Cout, int Cin) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+// Split-K partials -> parameter layout.  The partial sums (up to 296 splits) are walked in THEIR order (coalesced 256-byte
+// reads per split), `kZ` threads per output share the splits and combine through shared memory; only the final value is
+// scattered into dw[n][c][ky][kx].  (One thread per output walking all splits was ~36 us of pure load latency per call.)
+constexpr int kUnX = 64, kUnZ = 8;
+__global__ void __launch_bounds__(kUnX * kUnZ) unprep_conv_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw,
+                                                                  int Cout, int Cin) {
+  __shared__ float red[kUnZ][kUnX + 1];
   const long total = (long)Cout * Cin * 16;
-  if (i >= total) return;
-  const int kx = (int)(i & 3), ky = (int)((i >> 2) & 3);
-  const int c = (int)((i >> 4) % Cin), n = (int)((i >> 4) / Cin);
-  const long src = ((long)n * 16 + ky * 4 + kx) * Cin + c;
+  const long j = blockIdx.x * (long)kUnX + threadIdx.x;   // index in the fprop operand layout [n][ky][kx][c]
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[(long)z * total + src];
-  dw[i] = s;
-}
-__global__ void unprep_conv1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw, float* __restrict__ dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over dw[n][c][ky][kx], 32*3*16
-  if (i < 32 && dbias) {  // pad channel (q = 3) of tap (0,0): sum over pixels of dy[n] * 1.0 = bias gradient
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += part[z * (32 * 64) + i * 64 + 3];
-    dbias[i] = s;
+  if (j < total)
+    for (int z = threadIdx.y; z < splits; z += kUnZ) s += part[(long)z * total + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < total) {
+#pragma unroll
+    for (int y = 1; y < kUnZ; ++y) s += red[y][threadIdx.x];
+    const int c = (int)(j % Cin);
+    const int kyx = (int)((j / Cin) & 15), n = (int)(j / ((long)Cin * 16));
+    dw[((long)n * Cin + c) * 16 + kyx] = s;
   }
-  if (i >= 32 * 48) return;
-  const int kx = i & 3, ky = (i >> 2) & 3, c = (i >> 4) % 3, n = (i >> 4) / 3;
-  const int ky2 = ky >> 1, dy = ky & 1, px = kx >> 1, dx = kx & 1;
-  const int src = ((n * 2 + ky2) * 2 + px) * 16 + dy * 8 + dx * 4 + c;
+}
+__global__ void __launch_bounds__(kUnX * kUnZ) unprep_conv1_kernel(const float* __restrict__ part, int splits, float* __restrict__ dw,
+                                                                   float* __restrict__ dbias) {
+  __shared__ float red[kUnZ][kUnX + 1];
+  const int j = blockIdx.x * kUnX + threadIdx.x;          // operand index [n][ky2][px][q = dy*8+dx*4+c4], 32*64 entries
   float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += part[z * (32 * 64) + src];
-  dw[i] = s;
+  for (int z = threadIdx.y; z < splits; z += kUnZ) s += part[z * (32 * 64) + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 1; y < kUnZ; ++y) s += red[y][threadIdx.x];
+    const int q = j & 15, px = (j >> 4) & 1, ky2 = (j >> 5) & 1, n = j >> 6;
+    const int c = q & 3, dx = (q >> 2) & 1, dy = (q >> 3) & 1;
+    if (c < 3) dw[((n * 3 + c) * 4 + (2 * ky2 + dy)) * 4 + (2 * px + dx)] = s;
+    // pad channel (q = 3) of tap (0,0): sum over pixels of dy[n] * 1.0 = bias gradient
+    else if (dbias && (j & 63) == 3) dbias[n] = s;
+  }
 }
 // FC1 column permutation: reference column c*100+p  <->  operand column p*256+c
 __global__ void prep_fc1_kernel(const float* __restrict__ w, float* __restrict__ wg, int out, int tail, long ld) {
@@ -468,6 +527,14 @@ int gc_gather_obs_u8_s2d(const unsigned char* src, const long long* idx, float* 
   GC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)out & 15) == 0, "gc_gather_obs_u8_s2d: pointers must be 16-byte aligned");
   gather_obs_u8_s2d_kernel<<<dim3(kS2dH / kG8Rows, B), 256, 0, (cudaStream_t)stream>>>(src, idx, out);
   return gc::launch_status("gather_obs_u8_s2d_kernel");
+}
+
+int gc_gather_pair_mix_u8_s2d(const unsigned char* src_e, const long long* idx_e, const unsigned char* src_p, const long long* idx_p,
+                              const float* alpha, float* out, int B, void* stream) {
+  GC_REQUIRE(src_e && src_p && alpha && out && B > 0 && B <= 65535, "gc_gather_pair_mix_u8_s2d: bad arguments");
+  GC_REQUIRE((((uintptr_t)src_e | (uintptr_t)src_p | (uintptr_t)out) & 15) == 0, "gc_gather_pair_mix_u8_s2d: pointers must be 16-byte aligned");
+  gather_pair_mix_u8_s2d_kernel<<<dim3(kS2dH / kG8Rows, B), 256, 0, (cudaStream_t)stream>>>(src_e, idx_e, src_p, idx_p, alpha, out, B);
+  return gc::launch_status("gather_pair_mix_u8_s2d_kernel");
 }
 
 int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream) {
@@ -588,11 +655,11 @@ int gc_unprep_conv_wgrad(const float* part, int splits, float* dw, float* dbias,
   cudaStream_t st = (cudaStream_t)stream;
   if (layer1) {
     GC_REQUIRE(Cout == 32 && Cin == 3, "gc_unprep_conv_wgrad: layer1 expects 32x3x4x4");
-    unprep_conv1_kernel<<<6, 256, 0, st>>>(part, splits, dw, dbias);
+    unprep_conv1_kernel<<<(32 * 64) / kUnX, dim3(kUnX, kUnZ), 0, st>>>(part, splits, dw, dbias);
   } else {
     GC_REQUIRE(dbias == nullptr, "gc_unprep_conv_wgrad: the bias-gradient column exists only for layer 1");
     const long n = (long)Cout * Cin * 16;
-    unprep_conv_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(part, splits, dw, Cout, Cin);
+    unprep_conv_kernel<<<(int)((n + kUnX - 1) / kUnX), dim3(kUnX, kUnZ), 0, st>>>(part, splits, dw, Cout, Cin);
   }
   return gc::launch_status("unprep_conv_kernel");
 }

@@ -126,6 +126,7 @@ struct Plan {
 };
 
 constexpr int kSmemBudget = 225 * 1024;
+constexpr int kSmemFixed = 5120;   // mbarriers, TMEM slot, descriptor table (256 B), bias (2 KB), column sums (1 KB), 1 KB alignment slack
 
 // CTA-pair mode pays when the B tile is a large share of the per-k-iteration TMA rows (N >= 128) and needs an even
 // number of m-tiles (a pair works on m-tiles 2j, 2j+1 of the same n-tile) and the two-group bit-mask / plain epilogues.
@@ -164,14 +165,14 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     // two staging buffers per epilogue group (the TMA store of panel i drains while panel i+1 is formed) when that still
     // leaves a deep operand ring - in practice the small-tile streaming layers (conv1), whose epilogue is the bottleneck
     const int stage_b = p.a_bytes + p.b_bytes;
-    if ((kSmemBudget - (4 * 16384 + 4096 + resident)) / stage_b >= 6) p.nbuf = 4;
+    if ((kSmemBudget - (4 * 16384 + kSmemFixed + resident)) / stage_b >= 6) p.nbuf = 4;
   }
   if (p.acc_stages == 0) p.acc_stages = 2;
   p.tmem_cols = pow2_cols(p.acc_stages * bpan * 32);
   GC_REQUIRE(p.tmem_cols <= 512, "%s: accumulators need %d TMEM columns", what, p.tmem_cols);
   p.d_row_bytes = p.bn >= 32 ? 128 : p.bn * 4;
   const int stage = p.a_bytes + p.b_bytes;
-  const int fixed = p.nbuf * 16384 + 4096 + resident;  // staging + barriers/bias/alignment slack + resident weights
+  const int fixed = p.nbuf * 16384 + kSmemFixed + resident;  // staging + barriers/bias/column sums/alignment slack + resident weights
   int stages = (kSmemBudget - fixed) / stage;
   stages = std::min(stages, 8);
   GC_REQUIRE(stages >= 2, "%s: tile does not fit in shared memory (stage %d B, fixed %d B)", what, stage, fixed);
@@ -476,8 +477,10 @@ int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const f
 // 32-column output panel belongs to one class and is stored through that class's strided tensor map.
 // mask = LeakyReLU'(sign of mask_src at the output position).
 int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, const unsigned* mask_bits,
-                  float* dx, float slope, void* stream) {
+                  float* dx, float slope, float* dbias_in, int dbias_samples, void* stream) {
   if (int e = check_geom(g, "gc_conv_dgrad")) return e;
+  if (dbias_in) GC_REQUIRE(mask_bits && g->Cin >= 32 && (g->Cin & (g->Cin - 1)) == 0 && g->Cin <= 256,
+                           "gc_conv_dgrad: dbias_in needs the bit-mask epilogue and a power-of-two Cin in [32,256]");
   GC_REQUIRE(dy && wd && dx, "gc_conv_dgrad: null pointer");
   GC_REQUIRE(g->KH % g->S == 0 && g->KW % g->S == 0, "gc_conv_dgrad: taps must be a multiple of the stride");
   GC_REQUIRE(g->Cout % 32 == 0 && g->Cin % 16 == 0 && g->Cin <= 256, "gc_conv_dgrad: Cout%%32, Cin%%16, Cin<=256 required");
@@ -500,6 +503,10 @@ int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const
       p.bit_base[cls] = ((long)py * g->Wp + px) * g->Cin;
     }
     p.bit_str[0] = (long)g->S * g->Cin; p.bit_str[1] = (long)g->S * g->Wp * g->Cin; p.bit_str[2] = g->in_batch_stride;
+    if (dbias_in) {   // bias gradient of the layer below: column sums of the masked dx over the first dbias_samples samples
+      p.colsum_out = dbias_in; p.colsum_mask = g->Cin - 1; p.colsum_dim = 2;
+      p.colsum_limit = dbias_samples > 0 ? dbias_samples : g->B;
+    }
   };
   // Patch mode for the small layers (conv2, and conv1 in its stride-1 space-to-depth form): resident weights (all classes,
   // <= 128 KB) and one (8+1)x(16+1) patch of dy per 32-channel chunk serving the 4 taps (a,b') as shifted A views.
@@ -847,8 +854,11 @@ int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const floa
 
 // dx[m][n] = mask * sum_k dy[m][k] * w[k][n]   (w is the forward weight [out=K][in=N], read MN-major - no transpose)
 int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, const unsigned* mask_bits,
-                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, void* stream) {
+                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, float* colsum, int colsum_mod,
+                    int colsum_rows, void* stream) {
   GC_REQUIRE(dy && w && dx && M > 0 && N > 0 && K > 0, "gc_linear_dgrad: bad arguments");
+  if (colsum) GC_REQUIRE(mask_bits && colsum_mod >= 32 && colsum_mod <= 256 && (colsum_mod & (colsum_mod - 1)) == 0 && N % 32 == 0,
+                         "gc_linear_dgrad: colsum needs the bit-mask epilogue, N %% 32 == 0 and a power-of-two modulus in [32,256]");
   GC_REQUIRE(lddy % 4 == 0 && ldw % 4 == 0 && lddx % 4 == 0 && ldm % 4 == 0, "gc_linear_dgrad: pitches must be multiples of 4");
   Plan pl;
   GemmParams& p = pl.p;
@@ -889,6 +899,10 @@ int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const 
     p.row_box[0] = 128; p.row_box[1] = 1; p.row_box[2] = 1;
     p.row_ext[0][0] = M; p.row_ext[0][1] = 1; p.row_ext[0][2] = 1;
     p.bit_str[0] = ldm; p.bit_str[1] = 0; p.bit_str[2] = 0; p.bit_base[0] = 0;
+    if (colsum) {
+      p.colsum_out = colsum; p.colsum_mask = colsum_mod - 1; p.colsum_dim = 0;
+      p.colsum_limit = colsum_rows > 0 ? colsum_rows : M;
+    }
   }
   pl.grid = dim3(p.e0, p.f0, 1);
   return finish_and_launch(pl, (cudaStream_t)stream, "gc_linear_dgrad");

@@ -92,6 +92,12 @@ struct alignas(64) GemmParams {
   long bit_base[4];          // element offset of each output map's origin in that tensor
   float slope;
   const float* bias;
+  // Column sums of the stored (masked) output, accumulated into colsum_out[column & colsum_mask] (fp32 atomics): the bias
+  // gradient of the layer whose pre-activation gradient this dgrad produces, taken from the staged tile instead of a
+  // separate pass over the tensor.  Bit-mask epilogue only.  Rows whose coordinate `colsum_dim` (0..2, see row_box) is
+  // >= colsum_limit are stored but not summed (gradient-penalty rows of the critic batch).
+  float* colsum_out;         // nullable
+  int colsum_mask, colsum_dim, colsum_limit;
   // debug (GC_UMMA_STATS=1): per-CTA clocks each role spent waiting on its barriers, 8 counters per CTA; nullptr = off
   long long* stats;
 };

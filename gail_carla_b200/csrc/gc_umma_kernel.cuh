@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   // filled once by the MMA thread (the per-tap constant-bank lookups were ~100 clocks of its ~105 per MMA)
   uint32_t* s_btab = (uint32_t*)(((uintptr_t)(tmem_slot + 4) + 15) & ~(uintptr_t)15);
   float* s_bias = (float*)(s_btab + 64);  // nt*bn floats (<= 512) for bias epilogues
+  float* s_colsum = s_bias + 512;         // <= 256 per-channel column sums of the stored tiles (p.colsum_out)
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // provably warp-uniform
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages;
@@ -368,6 +369,9 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   }
   if ((p.epilogue == EPI_BIAS_LRELU || p.epilogue == EPI_BIAS) && p.nt * p.bn <= 512) {
     for (int i = threadIdx.x; i < p.nt * p.bn; i += blockDim.x) s_bias[i] = i < p.n_total ? __ldg(p.bias + i) : 0.f;
+  }
+  if (p.colsum_out != nullptr) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_colsum[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -692,6 +696,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const float slope = p.slope;
     const bool bias_smem = p.nt * p.bn <= 512;
     const bool want_bits = p.bits_out != nullptr && epi == EPI_BIAS_LRELU;
+    const bool want_colsum = p.colsum_out != nullptr && bitmask && swz && !m64;
+    const int cs_dim = p.colsum_dim, cs_limit = p.colsum_limit, cs_mask = p.colsum_mask;
     // fprop tiles: consecutive panels are consecutive 32-channel groups of the same pixels, i.e. consecutive bit words -
     // the word index and the clipping test are then formed once per tile instead of once per panel
     const bool simple_panels = !SLAB && p.cols_per_map == 0 && p.d.period == 0 && p.d.panel[0] == 32 && p.d.panel[1] == 0 &&
@@ -718,12 +724,14 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       for (int d = 0; d < 5; ++d) cd[d] = td_.c[d];
       // 32-bit word (in the bit tensor of the activation the mask describes) of this thread's row in panel q, or -1 if the
       // row is clipped.  Strides / extents of map 0 live in registers (hoisted above the tile loop).
+      bool in_limit = true;   // side result of bit_word: this row counts towards the column sums (p.colsum_limit)
       auto bit_word = [&](int q) -> long {
         int cq[5];
         const int mi = out_panel(cd, n_tile, q, cq);
         const int c1 = cq[1] + r0, c2 = cq[2] + r1, c3 = cq[3] + r2;
         const int x0 = mi == 0 ? ext0[0] : p.row_ext[mi][0], x1 = mi == 0 ? ext0[1] : p.row_ext[mi][1],
                   x2 = mi == 0 ? ext0[2] : p.row_ext[mi][2];
+        if (want_colsum) in_limit = (cs_dim == 0 ? c1 : (cs_dim == 1 ? c2 : c3)) < cs_limit;
         if (!r2_ok || c1 >= x0 || c2 >= x1 || c3 >= x2) return -1;
         const long base = mi == 0 ? bbase0 : p.bit_base[mi];
         return (base + cq[1] * bs0 + cq[2] * bs1 + cq[3] * bs2 + cq[0] + thread_bit_off) >> 5;
@@ -732,13 +740,17 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       // sub-tile mode: word of panel 0 without the clipping test; each panel tests its own shifted rows
       const long sw0 = (bbase0 + cd[1] * bs0 + cd[2] * bs1 + cd[3] * bs2 + cd[0] + thread_bit_off) >> 5;
       unsigned mbits[8];
+      unsigned cs_ok = 0u;   // bit q: this thread's row of panel q is stored and counts towards the column sums
       if (bitmask) {  // issued before waiting for the accumulator: the loads overlap the tile's mainloop
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           mbits[q] = 0u;
           if (q < n_panels) {
             const long wi = bit_word(q);
-            if (wi >= 0) mbits[q] = __ldg(p.bits_in + wi);
+            if (wi >= 0) {
+              mbits[q] = __ldg(p.bits_in + wi);
+              cs_ok |= in_limit ? (1u << q) : 0u;
+            }
           }
         }
       }
@@ -857,6 +869,22 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           tma_store_5d(&p.mapD[mi_st], buf, cq_st);
           tma_commit();
         }
+        if (want_colsum) {
+          // The tile is complete in the staging buffer: warp wq sums column `lane` over its own 32 rows (the ballot is the
+          // stored-and-counted flag of exactly those rows).  One 128-byte row per request: conflict-free with the swizzle.
+          const unsigned rows_ok = __ballot_sync(0xffffffffu, (cs_ok >> q) & 1u);
+          float cs = 0.f;
+          const uint32_t rbase = buf + (uint32_t)(wq * 32) * 128u, cchunk = (uint32_t)(lane >> 2), cword = (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if ((rows_ok >> rr) & 1u) {
+              float t;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(rbase + (uint32_t)rr * 128u + ((cchunk ^ (uint32_t)(rr & 7)) << 4) + cword) : "memory");
+              cs += t;
+            }
+          }
+          if (rows_ok) atomicAdd(s_colsum + ((col0 + lane) & cs_mask), cs);
+        }
         if (timed) { e_free += c1 - c0; e_ld += c2 - c1; e_math += c2a - c2; e_sts += c2b - c2a; e_bar += c3 - c2b; e_store += clock64() - c3; }
         if (++bi == nbuf) { bi = 0; bph ^= 1; }
       }
@@ -880,6 +908,12 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.colsum_out != nullptr) {   // this CTA's share of the column sums
+    for (int i = threadIdx.x; i <= p.colsum_mask; i += blockDim.x) {
+      const float v = s_colsum[i];
+      if (v != 0.f) atomicAdd(p.colsum_out + i, v);
+    }
+  }
   if constexpr (CTA2) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still signal / read it
   if (warp == 8) {
     if constexpr (CTA2) {

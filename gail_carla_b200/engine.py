@@ -212,6 +212,7 @@ class ConvStack:
         self.wf: List[torch.Tensor] = []
         self.wd: List[Optional[torch.Tensor]] = []
         self._dev = None
+        self.fused_dbias = True      # conv2-4 bias gradients from the dgrad epilogues (False: gc_colsum passes)
 
     def wname(self, i: int) -> str:
         return f"{self.prefix}main.{2 * (i - 1)}.weight"
@@ -254,14 +255,18 @@ class ConvStack:
             y = ws.F[row0:] if i == 4 else ws.A[i][row0:]
             A.conv_fprop(conv_geom(i, B), x, self.wf[i - 1], None, y, EPI_MASK, SLOPE, mask_src=y, mask_bits=self.bits(ws, i, row0))
 
-    def backward_data(self, ws: Workspace, B: int, row0: int = 0) -> None:
+    def backward_data(self, ws: Workspace, B: int, row0: int = 0, B_bias: int = 0) -> None:
         """delta_4 (= ws.dA[4], already multiplied by LeakyReLU'(a_4)) -> delta_3, delta_2, delta_1 for rows
-        [row0,row0+B); each dgrad epilogue applies LeakyReLU' of the layer it lands on."""
+        [row0,row0+B); each dgrad epilogue applies LeakyReLU' of the layer it lands on.  With B_bias > 0 the dgrads that
+        produce delta_3 and delta_2 also leave conv3's / conv2's bias gradient (sum of delta over the pixels of the first
+        B_bias samples) in the flat gradient buffer - taken from the staged output tiles, not from another pass."""
         dA = ws.grads()
         for i in (4, 3, 2):
             g = conv_geom4_compact(B) if i == 4 else conv_geom(i, B)
+            fused = B_bias > 0 and i > 2          # delta_1's bias gradient is a column of conv1's wgrad (see backward_params)
             A.conv_dgrad(g, dA[i][row0:], self.wd[i - 1], dA[i - 1][row0:], ws.A[i - 1][row0:], SLOPE,
-                         mask_bits=self.bits(ws, i - 1, row0))
+                         mask_bits=self.bits(ws, i - 1, row0),
+                         dbias_in=self.flat.g(self.bname(i - 1)) if fused else None, dbias_samples=B_bias if fused else 0)
 
     def input_grad(self, ws: Workspace, B: int, row0: int) -> None:
         """dX0 = conv1^T(delta_1) for rows [row0,row0+B): the dD/dx of algo/wdgail.py:85-91 (normalised-input space)."""
@@ -283,7 +288,9 @@ class ConvStack:
             fused_bias = i == 1 and B_bias > 0
             A.unprep_conv_wgrad(part, splits, self.flat.g(self.wname(i)), CONV_CH[i], CONV_CH[i - 1], i == 1,
                                 self.flat.g(self.bname(i)) if fused_bias else None)
-            if B_bias > 0 and not fused_bias:
+            # conv2-4: the bias gradients were summed by the dgrad epilogues that produced delta_2..delta_4
+            # (backward_data / the FC1 dgrad of the owning engine) when fused_dbias is on; else one column-sum pass each
+            if B_bias > 0 and not fused_bias and not self.fused_dbias:
                 rows = B_bias * (96 * 96, 46 * 46, 22 * 22, 100)[i - 1]
                 A.colsum(dA[i], CONV_CH[i], rows, CONV_CH[i], self.flat.g(self.bname(i)))
 

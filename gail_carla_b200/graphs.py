@@ -19,7 +19,18 @@ import torch
 
 from . import _abi as A
 
+import weakref
+
 ENABLED = True        # module switch (bench.py --no-graphs, the instrumented per-kernel timing pass)
+_ALL = weakref.WeakSet()
+
+
+def release_all() -> None:
+    """Drop every captured graph.  Call this (after a device synchronize) BEFORE ``torch.distributed.destroy_process_group()``:
+    graphs that captured NCCL collectives keep communicator resources alive, and tearing the process group down underneath
+    them blocked ProcessGroupNCCL's watchdog until it aborted the process (seen on B200, torch 2.11 / NCCL 2.28)."""
+    for g in list(_ALL):
+        g.reset()
 
 
 class _Entry:
@@ -36,6 +47,7 @@ class StepGraph:
         self.name = name
         self.entries = {}
         self.broken = False
+        _ALL.add(self)
 
     def reset(self) -> None:
         self.entries = {}

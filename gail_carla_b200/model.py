@@ -15,6 +15,7 @@ import torch.nn as nn
 from . import _abi as A
 from . import engine as E
 from ._abi import LDF, EPI_BIAS_LRELU
+from .graphs import StepGraph
 
 N_METRIC_FEAT = 13
 
@@ -136,13 +137,14 @@ class PolicyEngine:
         A.unprep_fc1_wgrad(self.dw1, 1, G("base.body.body.0.weight"), 512, N_METRIC_FEAT, LDF)
         A.colsum(d, 512, B, 512, G("base.body.body.0.bias"))
         # features: conv part masked by LeakyReLU'(a4) (-> delta_4); metric part feeds the embedding
+        fb = self.conv.fused_dbias           # conv4's bias gradient = per-channel sums of delta_4, from this dgrad's epilogue
         A.linear_dgrad(d, 512, self.w1, LDF, dA[4], E.FEAT, B, E.FEAT, 512, mask_src=ws.F, ldm=LDF, slope=E.SLOPE,
-                       mask_bits=ws.mbits[4])
+                       mask_bits=ws.mbits[4], colsum=G(self.conv.bname(4)) if fb else None, colsum_mod=256, colsum_rows=B)
         A.linear_dgrad(d, 512, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, B, 32, 512)
         A.metrics_features_bwd(ws.buf("metrics", ws.rows, 4), ws.dFt, 32, G("base.metrics_processor.road_option_embedding.weight"), B)
         if reducer is not None:     # embedding + every Linear are final; the convolutions come first in the flat order
             reducer.ready(self.flat, *self.flat.span("base.metrics_processor.road_option_embedding.weight"))
-        self.conv.backward_data(ws, B)
+        self.conv.backward_data(ws, B, B_bias=B if fb else 0)
         self.conv.backward_params(ws, B, B)
 
 
@@ -171,6 +173,8 @@ class Policy(nn.Module):
         self.max = torch.Tensor([1, 1])     # tools/model.py:22-23 (unused by the reference as well)
         self.min = torch.Tensor([-1, 0])
         self._engine: Optional[PolicyEngine] = None
+        self._act_graph = StepGraph("act")
+        self._act_state = None
 
     # the reference's drivers move the module around; parameters are re-flattened lazily
     @property
@@ -202,16 +206,42 @@ class Policy(nn.Module):
         return eng, eng.forward(B, training=training), B
 
     def act(self, obs, metrics, deterministic=False):
-        """tools/model.py:25-36 -> (value [B,1], action [B,2], action_log_probs [B,1])."""
+        """tools/model.py:25-36 -> (value [B,1], action [B,2], action_log_probs [B,1]).
+
+        This is the per-env-step call of the rollout loop (tools/learn.py:111-133): a batch of N envs, ~25 launches that
+        are each shorter than their launch overhead.  The inputs are copied into static device buffers and the whole
+        step (gather + normalise, trunk forward, sampling head) is replayed as one CUDA graph (graphs.StepGraph)."""
         with torch.no_grad():
-            eng, head, B = self._run(obs, metrics)
-            dev = head.device
+            eng = self.engine
+            eng.sync_params()
+            dev = eng.flat.flat.device
+            B = int(obs.shape[0])
+            u8 = obs.dtype == torch.uint8
+            st = getattr(self, "_act_state", None)
+            if st is None or st["B"] != B or st["u8"] != u8 or st["obs"].device != dev:
+                st = dict(B=B, u8=u8, obs=torch.zeros(B, 3, 192, 192, dtype=torch.uint8 if u8 else torch.float32, device=dev),
+                          met=torch.zeros(B, 4, device=dev), noise=torch.zeros(B, 2, device=dev), value=torch.empty(B, 1, device=dev),
+                          action=torch.empty(B, 2, device=dev), logp=torch.empty(B, 1, device=dev))
+                self._act_state = st
+            src = obs.as_subclass(torch.Tensor) if u8 else obs
+            st["obs"].copy_(src, non_blocking=True)
+            st["met"].copy_(metrics, non_blocking=True)
             # Normal.sample() of the reference = mean + std * N(0,1) drawn from the default generator; the draw stays on
             # the host generator (B x 2 floats) so a GPU run consumes the same random stream as the CPU oracle
-            noise = None if deterministic else torch.randn(B, 2).to(dev, non_blocking=True)
-            value = torch.empty(B, 1, device=dev); action = torch.empty(B, 2, device=dev); logp = torch.empty(B, 1, device=dev)
-            A.policy_act(head, noise, value, action, logp, B, self.base.logstd.tolist(), self.base.activation)
-            return value, action, logp
+            if not deterministic:
+                st["noise"].copy_(torch.randn(B, 2), non_blocking=True)
+            logstd, activation = self.base.logstd.tolist(), self.base.activation
+
+            def device_step():
+                eng.workspace(B)
+                eng.load_inputs(st["obs"], st["met"], None, B)
+                head = eng.forward(B)
+                A.policy_act(head, None if deterministic else st["noise"], st["value"], st["action"], st["logp"], B, logstd, activation)
+
+            ws = eng.workspace(B)
+            key = (ws.X0.data_ptr(), ws.rows, B, u8, bool(deterministic), eng.flat.flat.data_ptr(), st["obs"].data_ptr(), tuple(logstd), activation)
+            self._act_graph.run(key, device_step, dev)
+            return st["value"].clone(), st["action"].clone(), st["logp"].clone()
 
     def get_value(self, obs, metrics):
         """tools/model.py:41-43."""

@@ -72,6 +72,22 @@ class CriticEngine:
         A.gather_rows(met_rows, idx, ws.buf("metrics", ws.rows, 4)[row0:], B, 4, 4)
         A.gather_rows(act_rows, idx, ws.buf("actions", ws.rows, 2)[row0:], B, 2, 2)
 
+    def load_pair_mix(self, e_obs, e_met, e_act, e_idx, p_obs, p_met, p_act, p_idx, alpha, B: int) -> bool:
+        """Expert rows -> [0,B), policy rows -> [B,2B) and their mix-up -> [2B,3B) of the workspace.  With both image
+        sources uint8 this is ONE pass (gc_gather_pair_mix_u8_s2d) and returns True: update_step must then skip its own
+        mix-up launch.  Otherwise the two plain gathers run and it returns False."""
+        ws = self.ws
+        fused = e_obs.dtype == torch.uint8 and p_obs.dtype == torch.uint8
+        if fused:
+            A.gather_pair_mix(e_obs, e_idx, p_obs, p_idx, alpha, ws.X0, B)
+        else:
+            A.gather_obs_s2d(e_obs, e_idx, ws.X0, B)
+            A.gather_obs_s2d(p_obs, p_idx, ws.X0[B:], B)
+        m, a = ws.buf("metrics", ws.rows, 4), ws.buf("actions", ws.rows, 2)
+        A.gather_rows(e_met, e_idx, m, B, 4, 4); A.gather_rows(e_act, e_idx, a, B, 2, 2)
+        A.gather_rows(p_met, p_idx, m[B:], B, 4, 4); A.gather_rows(p_act, p_idx, a[B:], B, 2, 2)
+        return fused
+
     def tail_features(self, B: int, row0: int, mix_from: Optional[tuple] = None) -> None:
         """ProcessMetrics + action passthrough into F[:, 25600:]; ``mix_from=(row_e,row_p,alpha)`` mixes the raw inputs."""
         ws = self.ws
@@ -97,7 +113,8 @@ class CriticEngine:
         self.conv.forward(self.ws, rows, training=training)
         return self.trunk_forward(rows)
 
-    def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0, norm=None, reducer=None) -> None:
+    def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0, norm=None, reducer=None,
+                    premixed: bool = False) -> None:
         """Rows [0,B) expert, [B,2B) policy already loaded.  Builds the mix-up rows, runs forward + the full
         backward (Wasserstein part + gradient penalty) and leaves the gradients in the flat buffer.
         `norm`: rows the batch means run over (default B; the global minibatch size when B is one rank's share of it).
@@ -105,7 +122,8 @@ class CriticEngine:
         ws, P, G, H_ = self.ws, self.flat.p, self.flat.g, self.hidden
         R = 3 * B
         # ---- forward over expert | policy | mix-up (algo/wdgail.py:116,121,66-82)
-        A.mixup(ws.X0, ws.X0[B:], alpha, ws.X0[2 * B:], B, S2D_PER_SAMPLE)
+        if not premixed:       # (load_pair_mix already wrote the mix-up rows)
+            A.mixup(ws.X0, ws.X0[B:], alpha, ws.X0[2 * B:], B, S2D_PER_SAMPLE)
         self.tail_features(B, 0); self.tail_features(B, B); self.tail_features(B, 2 * B, mix_from=(0, B, alpha))
         d = self.forward(R, training=True)
         dd = ws.buf("dd", ws.rows)
@@ -118,13 +136,14 @@ class CriticEngine:
         A.small_linear_bwd(H, LDH, P("trunk.2.weight"), dd, 1, dH, LDH, G("trunk.2.weight"), G("trunk.2.bias"), R, 2 * B, 1,
                            H_, E.SLOPE)
         # delta_4 for all rows; metric/action columns only for the rows that carry loss (expert, policy)
+        fb = self.conv.fused_dbias     # conv2-4 bias gradients (expert + policy rows only) from the dgrad epilogues
         A.linear_dgrad(dH, LDH, self.w1, LDF, dA[4], E.FEAT, R, E.FEAT, H_, mask_src=ws.F, ldm=LDF, slope=E.SLOPE,
-                       mask_bits=ws.mbits[4])
+                       mask_bits=ws.mbits[4], colsum=G(self.conv.bname(4)) if fb else None, colsum_mod=256, colsum_rows=2 * B)
         A.linear_dgrad(dH, LDH, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, 2 * B, 32, H_)
         m = ws.buf("metrics", ws.rows, 4)
         emb_g = G("metrics_processor.road_option_embedding.weight")
         A.metrics_features_bwd(m, ws.dFt, 32, emb_g, 2 * B)
-        self.conv.backward_data(ws, R)
+        self.conv.backward_data(ws, R, B_bias=2 * B if fb else 0)
         # ---- gradient penalty: g = dD/dx on the mix-up rows, u = d gp/d g, second-order forward chain in place
         self.conv.input_grad(ws, B, 2 * B)
         A.grad_penalty(dA[0][2 * B:], ws.X0[2 * B:], acc[4:], B, S2D_PER_SAMPLE, lambda_, E.INV_STD, norm)
@@ -384,10 +403,12 @@ class Discriminator(nn.Module):
         acc, alpha_buf = self._acc, self._alpha_buf
         acc.zero_()
 
+        state = {"premixed": False}
+
         def device_step():
             """Forward + full backward + optimiser step on the 2B rows already gathered into the workspace; reads only
             device-resident state (alpha_buf, Adam's scalars), so it is captured once and replayed (graphs.StepGraph)."""
-            eng.update_step(B, alpha_buf, acc, reducer=opt.reducer)
+            eng.update_step(B, alpha_buf, acc, reducer=opt.reducer, premixed=state["premixed"])
             opt.step(from_device_hyper=True)
             eng.dirty = True
             eng.sync_params()
@@ -407,11 +428,10 @@ class Discriminator(nn.Module):
                 opt.advance()
                 if not exact:                      # fixed-shape step: inputs gathered eagerly, the rest replayed as a graph
                     ws = eng.workspace(3 * B)
-                    eng.load_inputs(e_obs, e_met, e_act, e_idx, B, 0)
-                    release()
-                    eng.load_inputs(obs_rows, met_rows, act_rows, idx, B, B)
                     alpha_buf.copy_(alpha, non_blocking=True)
-                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), world, self.max_grad_norm)
+                    state["premixed"] = eng.load_pair_mix(e_obs, e_met, e_act, e_idx, obs_rows, met_rows, act_rows, idx, alpha_buf, B)
+                    release()
+                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), world, self.max_grad_norm, state["premixed"])
                     self._graph.run(key, device_step, dev)
                     n += B * world
                     continue

@@ -82,6 +82,12 @@ int gc_gather_obs_s2d(const float* src, const long long* idx, float* out, int B,
  * image to uint8 and ToTensor() divides by 255): out = ((float)src/255 - mean)/std, bit-identical to decoding first. */
 int gc_gather_obs_u8_s2d(const unsigned char* src, const long long* idx, float* out, int B, void* stream);
 
+/* One critic minibatch in one pass (algo/wdgail.py:66-80,116,121), both sources uint8 tables: out rows [0,B) = expert images
+ * src_e[idx_e[b]], rows [B,2B) = policy images src_p[idx_p[b]], rows [2B,3B) = alpha[b]*expert + (1-alpha[b])*policy, all as
+ * gc_gather_obs_u8_s2d writes them (the mix equals gc_mixup applied to the first two row blocks, bit for bit). */
+int gc_gather_pair_mix_u8_s2d(const unsigned char* src_e, const long long* idx_e, const unsigned char* src_p, const long long* idx_p,
+                              const float* alpha, float* out, int B, void* stream);
+
 /* out[b, 0:width] = src[idx[b], 0:width] (idx nullable), out row pitch ldo - tools/storage.py:66-76 scalar columns. */
 int gc_gather_rows(const float* src, const long long* idx, float* out, int B, int width, long ldo, void* stream);
 
@@ -190,9 +196,12 @@ typedef struct gc_conv_geom {
  * second-order chain of the gradient penalty, algo/wdgail.py:85-97). */
 int gc_conv_fprop(const gc_conv_geom* g, const float* x, const float* w, const float* bias, const float* mask_src,
                   unsigned* mask_bits, float* y, int epilogue, float slope, void* stream);
-/* data gradient: dx = LeakyReLU'(mask_src) * conv_transpose(dy, w); wd in the dgrad operand layout. */
+/* data gradient: dx = LeakyReLU'(mask_src) * conv_transpose(dy, w); wd in the dgrad operand layout.
+ * dbias_in (nullable, needs mask_bits): dbias_in[c] += sum over the pixels of the first `dbias_samples` samples (<= 0: all) of
+ * the masked dx[.., c] - dx is the pre-activation gradient of the layer below, so this is that layer's bias gradient
+ * (nn.Conv2d bias, tools/model.py:137-143), summed from the output tiles while they are staged for the store. */
 int gc_conv_dgrad(const gc_conv_geom* g, const float* dy, const float* wd, const float* mask_src, const unsigned* mask_bits,
-                  float* dx, float slope, void* stream);
+                  float* dx, float slope, float* dbias_in, int dbias_samples, void* stream);
 /* weight gradient partials [splits][Cout][KH][KW*Cin]; gc_conv_wgrad_splits suggests `splits` for a geometry. */
 int gc_conv_wgrad_splits(const gc_conv_geom* g);
 int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float* dw_partial, int splits, void* stream);
@@ -200,9 +209,12 @@ int gc_conv_wgrad(const gc_conv_geom* g, const float* dy, const float* x, float*
 /* nn.Linear forward (tools/model.py:93-99,110-113; algo/wdgail.py:27-31): y[z] = epi(x[:, Kz] w[:, Kz]^T). */
 int gc_linear_fwd(const float* x, long ldx, const float* w, long ldw, const float* bias, float* y, long ldy, int M, int N, int K,
                   int epilogue, float slope, int splits, void* stream);
-/* dx[M,N] = LeakyReLU'(mask_src) * dy[M,K] w[K,N]  (w = forward weight [out=K, in=N]). */
+/* dx[M,N] = LeakyReLU'(mask_src) * dy[M,K] w[K,N]  (w = forward weight [out=K, in=N]).
+ * colsum (nullable, needs mask_bits): colsum[n % colsum_mod] += sum over the first `colsum_rows` rows (<= 0: all) of the
+ * masked dx[.., n] - with dx the NHWC conv4 feature gradient [M, 100 pixels x 256 channels] this is conv4's bias gradient. */
 int gc_linear_dgrad(const float* dy, long lddy, const float* w, long ldw, const float* mask_src, const unsigned* mask_bits,
-                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, void* stream);
+                    long ldm, float* dx, long lddx, int M, int N, int K, float slope, float* colsum, int colsum_mod,
+                    int colsum_rows, void* stream);
 /* dw[z][M,N] = sum_{rows in split z} dy[row,M]^T x[row,N]. */
 int gc_linear_wgrad(const float* dy, long lddy, const float* x, long ldx, float* dw, long lddw, int M, int N, int K, int splits,
                     void* stream);

@@ -150,6 +150,14 @@ def gather_obs_s2d(src, idx, out, B):
     out.view(-1)[:B * 96 * 96 * 16] = x4.reshape(-1)
 
 
+def gather_pair_mix(src_e, idx_e, src_p, idx_p, alpha, out, B):
+    per = 96 * 96 * 16
+    o = out.view(-1)
+    gather_obs_s2d(src_e, idx_e, o[:B * per], B)
+    gather_obs_s2d(src_p, idx_p, o[B * per:2 * B * per], B)
+    mixup(o[:B * per], o[B * per:2 * B * per], alpha, o[2 * B * per:3 * B * per], B, per)
+
+
 def gather_rows(src, idx, out, B, width, ldo):
     rows = src.reshape(-1, width)
     _v2(out, B, width, ldo).copy_(rows[idx[:B]] if idx is not None else rows[:B])
@@ -345,7 +353,7 @@ def _w_from_dgrad_layout(g, wd):
     return t.permute(5, 2, 3, 0, 4, 1).reshape(g.Cout, g.Cin, g.KH, g.KW)                           # n,c,(a,py),(b',px)
 
 
-def conv_dgrad(geom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None):
+def conv_dgrad(geom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None, dbias_in=None, dbias_samples=0):
     g = geom
     w = _w_from_dgrad_layout(g, wd)
     d = _out_view(g, dy)[:, :g.OH, :g.OW].permute(0, 3, 1, 2)
@@ -356,6 +364,9 @@ def conv_dgrad(geom, dy, wd, dx, mask_src=None, slope=0.2, mask_bits=None):
     if mask_src is not None:
         full = full * _slope_mask(_in_view(g, mask_src)[:, :g.H, :g.W], slope)
     _in_view(g, dx)[:, :g.H, :g.W].copy_(full)
+    if dbias_in is not None:
+        nb = dbias_samples if dbias_samples > 0 else g.B
+        dbias_in.view(-1)[:g.Cin].add_(full[:nb].sum((0, 1, 2)))
 
 
 def conv_wgrad_splits(geom) -> int:
@@ -386,11 +397,15 @@ def linear_fwd(x, ldx, w, ldw, bias, y, ldy, M, N, K, epilogue, slope=0.2, split
     o[0] = r
 
 
-def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None):
+def linear_dgrad(dy, lddy, w, ldw, dx, lddx, M, N, K, mask_src=None, ldm=0, slope=0.2, mask_bits=None, colsum=None, colsum_mod=0,
+                 colsum_rows=0):
     r = _v2(dy, M, K, lddy) @ _v2(w, K, N, ldw)
     if mask_src is not None:
         r = r * _slope_mask(_v2(mask_src, M, N, ldm), slope)
     _v2(dx, M, N, lddx).copy_(r)
+    if colsum is not None:
+        nr = colsum_rows if colsum_rows > 0 else M
+        colsum.view(-1)[:colsum_mod].add_(r[:nr].reshape(nr, N // colsum_mod, colsum_mod).sum((0, 1)))
 
 
 def linear_wgrad(dy, lddy, x, ldx, dw, lddw, M, N, K, splits=1):

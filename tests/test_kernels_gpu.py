@@ -152,6 +152,21 @@ def test_gather_mixup_metrics():
         o_ref = torch.zeros(B, 96, 96, 16); E.gather_obs_s2d(src8, ix, o_ref, B)
         close(o8, o_ref, 1e-6, 1e-6, "gather_obs uint8")
         assert (o8.view(B, 96, 96, 4, 4)[..., 3] == 1).all(), "pad channel must hold 1.0"
+    # fused critic minibatch: expert rows | policy rows | mix-up in one pass == the two uint8 gathers + gc_mixup, bit for bit
+    srcp = torch.randint(0, 256, (rows, 3, 192, 192), generator=g, dtype=torch.uint8)
+    idx_p = torch.tensor([1, 1, 6, 2, 0]); al8 = torch.rand(B, generator=g)
+    per = 96 * 96 * 16
+    fused = torch.zeros(3 * B, per, device=DEV)
+    A.gather_pair_mix(src8.to(DEV), idx.to(DEV), srcp.to(DEV), idx_p.to(DEV), al8.to(DEV), fused, B)
+    sep = torch.zeros(3 * B, per, device=DEV)
+    A.gather_obs_s2d(src8.to(DEV), idx.to(DEV), sep, B); A.gather_obs_s2d(srcp.to(DEV), idx_p.to(DEV), sep[B:], B)
+    A.mixup(sep, sep[B:], al8.to(DEV), sep[2 * B:], B, per)
+    close(fused, sep, 0, 0, "gather_pair_mix vs gather + gather + mixup")
+    fused_none = torch.zeros(3 * B, per, device=DEV)
+    A.gather_pair_mix(src8.to(DEV), None, srcp.to(DEV), None, al8.to(DEV), fused_none, B)
+    A.gather_obs_s2d(src8.to(DEV), None, sep, B); A.gather_obs_s2d(srcp.to(DEV), None, sep[B:], B)
+    A.mixup(sep, sep[B:], al8.to(DEV), sep[2 * B:], B, per)
+    close(fused_none, sep, 0, 0, "gather_pair_mix (no index) vs separate kernels")
     s2 = torch.randn(rows, 4, generator=g)
     o_ref = torch.zeros(B, 8); E.gather_rows(s2, idx, o_ref, B, 4, 8)
     o = torch.zeros(B, 8, device=DEV); A.gather_rows(s2.to(DEV), idx.to(DEV), o, B, 4, 8)

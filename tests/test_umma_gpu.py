@@ -103,3 +103,46 @@ def test_bitmask_path_equals_fp32_mask_path(layer):
         E_.conv_dgrad(g, dy, wd, dx_ref, act, 0.5)
         v = lambda t: E_._in_view(g, t)[:, :g.H, :g.W]
         assert torch.equal(v(dx.cpu()), v(dx_ref))
+
+
+def _bits_of(act):
+    pos = (act > 0).view(-1, 32).to(torch.int64)
+    b = (pos << torch.arange(32)).sum(1)
+    return torch.where(b >= 2 ** 31, b - 2 ** 32, b).to(torch.int32)
+
+
+@pytest.mark.parametrize("layer,B,nb", [(2, 3, 2), (3, 5, 3), (4, 7, 7), (4, 131, 100), (3, 40, 0)])
+def test_dgrad_epilogue_bias_gradient_is_exact(layer, B, nb):
+    """gc_conv_dgrad(dbias_in=...): per-channel sums of the masked dx over the first `nb` samples, taken from the staged
+    output tiles (integer inputs -> bit-exact against the CPU statement; samples >= nb are stored but not summed; clipped
+    rows of partial tiles and the phantom tile of CTA-pair mode do not count)."""
+    from gail_carla_b200 import _abi as A
+    from oracle import abi_emu as E_
+    g = P.geom(layer, B)
+    nin, nout = B * g.in_batch_stride, B * g.out_batch_stride
+    Kw = g.KH * g.KW * g.Cin
+    act = P.ints((nin,), seed=9)
+    dy = P.ints((nout,), -1, 2, seed=11); wd = P.ints((g.Cout * Kw,), -1, 2, seed=13)
+    dy = dy * (torch.rand(nout, generator=torch.Generator().manual_seed(5)) < 0.25)      # sparse: keeps every sum exact in fp32
+    dx = torch.zeros(nin, device="cuda"); dx_ref = torch.zeros(nin)
+    db = torch.full((g.Cin,), 3.0, device="cuda"); db_ref = torch.full((g.Cin,), 3.0)       # accumulates (+=)
+    A.conv_dgrad(g, dy.cuda(), wd.cuda(), dx, act.cuda(), 0.5, mask_bits=_bits_of(act).cuda(), dbias_in=db, dbias_samples=nb)
+    E_.conv_dgrad(g, dy, wd, dx_ref, act, 0.5, dbias_in=db_ref, dbias_samples=nb)
+    v = lambda t: E_._in_view(g, t)[:, :g.H, :g.W]
+    assert torch.equal(v(dx.cpu()), v(dx_ref))
+    assert db_ref.abs().max() < 2 ** 22 and torch.equal(db.cpu(), db_ref), (db.cpu() - db_ref).abs().max()
+
+
+@pytest.mark.parametrize("M,rows", [(300, 200), (4096, 4096), (517, 0)])
+def test_linear_dgrad_epilogue_column_sums_are_exact(M, rows):
+    from gail_carla_b200 import _abi as A
+    from oracle import abi_emu as E_
+    N, K, mod = 1024, 96, 256
+    dy = P.ints((M, K), -1, 2, seed=1); w = P.ints((K, N), -1, 2, seed=2); act = P.ints((M, N), seed=3)
+    dx = torch.zeros(M, N, device="cuda"); dx_ref = torch.zeros(M, N)
+    cs = torch.zeros(mod, device="cuda"); cs_ref = torch.zeros(mod)
+    A.linear_dgrad(dy.cuda(), K, w.cuda(), N, dx, N, M, N, K, mask_src=act.cuda(), ldm=N, slope=0.5, mask_bits=_bits_of(act).cuda(),
+                   colsum=cs, colsum_mod=mod, colsum_rows=rows)
+    E_.linear_dgrad(dy, K, w, N, dx_ref, N, M, N, K, mask_src=act, ldm=N, slope=0.5, colsum=cs_ref, colsum_mod=mod, colsum_rows=rows)
+    assert torch.equal(dx.cpu(), dx_ref)
+    assert cs_ref.abs().max() < 2 ** 22 and torch.equal(cs.cpu(), cs_ref), (cs.cpu() - cs_ref).abs().max()
