@@ -217,12 +217,16 @@ class Policy(nn.Module):
             dev = eng.flat.flat.device
             B = int(obs.shape[0])
             u8 = obs.dtype == torch.uint8
-            st = getattr(self, "_act_state", None)
-            if st is None or st["B"] != B or st["u8"] != u8 or st["obs"].device != dev:
-                st = dict(B=B, u8=u8, obs=torch.zeros(B, 3, 192, 192, dtype=torch.uint8 if u8 else torch.float32, device=dev),
+            # static staging buffers, one set per (batch size, dtype, device) and kept for the module's lifetime: a captured
+            # graph holds their addresses, so they must never be re-created behind it
+            if self._act_state is None:
+                self._act_state = {}
+            st = self._act_state.get((B, u8, str(dev)))
+            if st is None:
+                st = dict(obs=torch.zeros(B, 3, 192, 192, dtype=torch.uint8 if u8 else torch.float32, device=dev),
                           met=torch.zeros(B, 4, device=dev), noise=torch.zeros(B, 2, device=dev), value=torch.empty(B, 1, device=dev),
                           action=torch.empty(B, 2, device=dev), logp=torch.empty(B, 1, device=dev))
-                self._act_state = st
+                self._act_state[(B, u8, str(dev))] = st
             src = obs.as_subclass(torch.Tensor) if u8 else obs
             st["obs"].copy_(src, non_blocking=True)
             st["met"].copy_(metrics, non_blocking=True)
@@ -239,7 +243,8 @@ class Policy(nn.Module):
                 A.policy_act(head, None if deterministic else st["noise"], st["value"], st["action"], st["logp"], B, logstd, activation)
 
             ws = eng.workspace(B)
-            key = (ws.X0.data_ptr(), ws.rows, B, u8, bool(deterministic), eng.flat.flat.data_ptr(), st["obs"].data_ptr(), tuple(logstd), activation)
+            key = (ws.X0.data_ptr(), ws.rows, B, u8, bool(deterministic), eng.flat.flat.data_ptr(), tuple(logstd), activation) + \
+                tuple(st[k].data_ptr() for k in ("obs", "met", "noise", "value", "action", "logp"))
             self._act_graph.run(key, device_step, dev)
             return st["value"].clone(), st["action"].clone(), st["logp"].clone()
 

@@ -75,10 +75,15 @@ class PPO():
         n_updates = 0
         n_bc_rows = 0
         # per-object device state the (replayable) step reads / writes: loss sums, advantage statistics, row indices
-        if getattr(self, "_dev_state", None) is None or self._dev_state[0].device != dev or self._dev_state[2].numel() != B:
-            self._dev_state = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev),
-                               torch.zeros(B, dtype=torch.int64, device=dev))
-        acc, stats_buf, idx_buf = self._dev_state
+        # (kept per (batch size, device) for the object's lifetime: a captured graph holds their addresses)
+        if self._dev_state is None:
+            self._dev_state = {}
+        if (B, str(dev)) not in self._dev_state:
+            self._dev_state[(B, str(dev))] = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev),
+                                              torch.zeros(B, dtype=torch.int64, device=dev))
+        acc, stats_buf, idx_buf = self._dev_state[(B, str(dev))]
+        if not eng.flat.grad_clean:        # a replayed step assumes the zeroed gradient buffer the previous step left behind
+            eng.flat.grad.zero_(); eng.flat.grad_clean = True
         acc.zero_()
         stats_buf.copy_(stats)
         opt = self.optimizer
@@ -118,8 +123,9 @@ class PPO():
                 if not use_bc and not exact:        # the common, fixed-shape step: replayed as one CUDA graph
                     idx_buf.copy_(idx, non_blocking=True)
                     ws = eng.workspace(B)
-                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), obs_rows.data_ptr(), ret_rows.data_ptr(), world,
-                           clipped, clip, vcoef, tuple(logstd), act, self.max_grad_norm)
+                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), eng.flat.grad.data_ptr(), world, clipped, clip, vcoef,
+                           tuple(logstd), act, self.max_grad_norm, opt.device_hyper(eng.flat).data_ptr()) + \
+                        tuple(t.data_ptr() for t in (obs_rows, met_rows, act_rows, vp_rows, ret_rows, lp_rows, acc, stats_buf, idx_buf))
                     self._graph.run(key, device_step, dev)
                     n_updates += 1
                     continue

@@ -183,7 +183,7 @@ class Discriminator(nn.Module):
         self.ret_rms = RunningMeanStd(shape=())     # constructed and never used, as in algo/wdgail.py:37-38
         self.exact_sharding = False                 # multi-GPU exact mode, see PPO.exact_sharding
         self._graph = StepGraph("critic")
-        self._alpha_buf = self._acc = None
+        self._alpha_buf = None
 
     @property
     def engine(self) -> CriticEngine:
@@ -397,11 +397,15 @@ class Discriminator(nn.Module):
         opt = self.optimizer
         if n_batches:
             opt.begin_schedule(n_batches)
-        if getattr(self, "_alpha_buf", None) is None or self._alpha_buf.device != dev or self._alpha_buf.numel() != B:
-            self._alpha_buf = torch.zeros(B, device=dev)
-            self._acc = torch.zeros(8, dtype=torch.float64, device=dev)
-        acc, alpha_buf = self._acc, self._alpha_buf
+        # static device state of the replayable step, kept per (batch size, device) for the module's lifetime
+        if self._alpha_buf is None:
+            self._alpha_buf = {}
+        if (B, str(dev)) not in self._alpha_buf:
+            self._alpha_buf[(B, str(dev))] = (torch.zeros(8, dtype=torch.float64, device=dev), torch.zeros(B, device=dev))
+        acc, alpha_buf = self._alpha_buf[(B, str(dev))]
         acc.zero_()
+        if not eng.flat.grad_clean:        # a replayed step assumes the zeroed gradient buffer the previous step left behind
+            eng.flat.grad.zero_(); eng.flat.grad_clean = True
 
         state = {"premixed": False}
 
@@ -431,7 +435,8 @@ class Discriminator(nn.Module):
                     alpha_buf.copy_(alpha, non_blocking=True)
                     state["premixed"] = eng.load_pair_mix(e_obs, e_met, e_act, e_idx, obs_rows, met_rows, act_rows, idx, alpha_buf, B)
                     release()
-                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), world, self.max_grad_norm, state["premixed"])
+                    key = (ws.X0.data_ptr(), ws.rows, B, eng.flat.flat.data_ptr(), eng.flat.grad.data_ptr(), world, self.max_grad_norm,
+                           state["premixed"], acc.data_ptr(), alpha_buf.data_ptr(), opt.device_hyper(eng.flat).data_ptr())
                     self._graph.run(key, device_step, dev)
                     n += B * world
                     continue
