@@ -363,7 +363,7 @@ def cpu_baseline_sample():
 
 def multi_gpu_parity(dev, rank, world):
     """Hardware check of the multi-GPU semantics: a small rollout of 2*world envs x 16 steps is
-    updated once (Discriminator.update + predict_reward + GAE + PPO.update, global minibatches of 32 rows) by `world`
+    updated once (Discriminator.update + predict_reward + GAE + PPO.update, global minibatches of 16*world rows) by `world`
     ranks in exact-sharding mode, and rank 0 then replays the same update as ONE process on the concatenated envs
     from the same seeds.  Reports the largest parameter / tuple / returns deviations between the two runs (the sharded
     run sums per-rank partial gradients over NCCL, the replay sums them inside one wgrad launch - TF32 products, fp32
@@ -372,7 +372,8 @@ def multi_gpu_parity(dev, rank, world):
     import gail_carla_b200 as G
     from gail_carla_b200 import synthetic, optim
     from gail_carla_b200.driver import update_iteration
-    T, Nl, Bglob = 16, 2, 32
+    T, Nl = 16, 2
+    Bglob = 16 * world          # ~16 +- 4 rows of every global minibatch per rank (binomial shares; an empty share is legal too)
     N = Nl * world
     sp, asp = NS(shape=(4,)), NS(shape=(2,))
 
@@ -451,7 +452,9 @@ def run_b200(args):
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+            # a collective that does not complete within 5 minutes is a bug: fail the run instead of stalling it
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(minutes=5))
             warm = torch.zeros(1, device=dev)
             dist.all_reduce(warm)
             torch.cuda.synchronize()
@@ -463,7 +466,12 @@ def run_b200(args):
     if args.no_graphs:
         from gail_carla_b200 import graphs as _graphs
         _graphs.ENABLED = False
-    parity_multi = multi_gpu_parity(dev, rank, world) if world > 1 else None
+    parity_multi = None
+    if world > 1 and not args.no_parity:
+        try:
+            parity_multi = multi_gpu_parity(dev, rank, world)
+        except Exception as ex:      # a failed check is reported in the line, it must not take the measurement down
+            parity_multi = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
     prof = Profiler(A)
     pk = peaks()
     c = dict(CONFIGS[args.config])
@@ -777,6 +785,7 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch-on-CUDA yardstick")
     ap.add_argument("--obs-store", default="u8", choices=["u8", "f32"],
                     help="rollout observation store: uint8 bytes (lossless, observations are uint8/255) or the reference's fp32")
+    ap.add_argument("--no-parity", action="store_true", help="multi-GPU runs: skip the exact-sharding parity check")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

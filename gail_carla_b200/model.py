@@ -109,6 +109,15 @@ class PolicyEngine:
         return out
 
     # ---- backward ----------------------------------------------------------------------------------------
+    EARLY_BUCKET = "base.metrics_processor.road_option_embedding.weight"   # first parameter of the early all-reduce bucket
+
+    def zero_contribution(self, reducer=None) -> None:
+        """This rank holds no row of the current global minibatch (exact sharding): its gradient is zero, but it must issue
+        the SAME sequence of collectives as the ranks that ran a backward pass - same buckets, same order."""
+        self.flat.begin_backward()
+        if reducer is not None:
+            reducer.ready(self.flat, *self.flat.span(self.EARLY_BUCKET))
+
     def backward(self, B: int, d_head: torch.Tensor, reducer=None) -> None:
         """d loss / d head_out [B,4] -> gradients of every parameter (written into the flat grad buffer).
         `reducer` (optim.GradReducer): told when a slice of the gradient buffer is final, so the multi-GPU all-reduce of
@@ -143,7 +152,7 @@ class PolicyEngine:
         A.linear_dgrad(d, 512, self.w1[:, E.FEAT:], LDF, ws.dFt, 32, B, 32, 512)
         A.metrics_features_bwd(ws.buf("metrics", ws.rows, 4), ws.dFt, 32, G("base.metrics_processor.road_option_embedding.weight"), B)
         if reducer is not None:     # embedding + every Linear are final; the convolutions come first in the flat order
-            reducer.ready(self.flat, *self.flat.span("base.metrics_processor.road_option_embedding.weight"))
+            reducer.ready(self.flat, *self.flat.span(self.EARLY_BUCKET))
         self.conv.backward_data(ws, B, B_bias=B if fb else 0)
         self.conv.backward_params(ws, B, B)
 

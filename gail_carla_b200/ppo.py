@@ -167,7 +167,7 @@ class PPO():
                                    0.0, 0.0, float(self.gamma), 1, norm=Be_norm if exact else None)
                     eng.backward(Bl + Be, d_head, reducer=opt.reducer)
                 else:            # this rank owns no member of the global minibatch: it contributes a zero gradient
-                    eng.flat.begin_backward()
+                    eng.zero_contribution(opt.reducer)
                 n_bc_rows += Be_norm if exact else Be
                 opt.step(from_device_hyper=True)
                 eng.dirty = True

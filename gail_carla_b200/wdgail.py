@@ -113,6 +113,15 @@ class CriticEngine:
         self.conv.forward(self.ws, rows, training=training)
         return self.trunk_forward(rows)
 
+    EARLY_BUCKET = "metrics_processor.road_option_embedding.weight"   # first parameter of the early all-reduce bucket
+
+    def zero_contribution(self, reducer=None) -> None:
+        """No row of the current global minibatch on this rank (exact sharding): zero gradient, but the same sequence of
+        collectives as the ranks that ran update_step (same buckets, same order)."""
+        self.flat.begin_backward()
+        if reducer is not None:
+            reducer.ready(self.flat, *self.flat.span(self.EARLY_BUCKET))
+
     def update_step(self, B: int, alpha: torch.Tensor, acc: torch.Tensor, lambda_: float = 10.0, norm=None, reducer=None,
                     premixed: bool = False) -> None:
         """Rows [0,B) expert, [B,2B) policy already loaded.  Builds the mix-up rows, runs forward + the full
@@ -158,7 +167,7 @@ class CriticEngine:
         A.unprep_fc1_wgrad(self.dw1, 1, G("trunk.0.weight"), H_, TAIL, LDF)
         A.colsum(dH, LDH, 2 * B, H_, G("trunk.0.bias"))
         if reducer is not None:      # embedding + trunk are final; only the convolution weight gradients remain
-            reducer.ready(self.flat, *self.flat.span("metrics_processor.road_option_embedding.weight"))
+            reducer.ready(self.flat, *self.flat.span(self.EARLY_BUCKET))
         self.conv.backward_params(ws, R, 2 * B)
 
 
@@ -449,7 +458,7 @@ class Discriminator(nn.Module):
                     eng.update_step(Bl, alpha, acc, norm=B, reducer=opt.reducer)
                 else:              # this rank owns no member of the global minibatch: zero gradient, still all-reduces
                     release()
-                    eng.flat.begin_backward()
+                    eng.zero_contribution(opt.reducer)
                 opt.step(from_device_hyper=True)
                 eng.dirty = True
                 eng.sync_params()

@@ -143,3 +143,88 @@ def test_two_rank_exact_sharding_matches_single_process_reference():
         assert p.exitcode == 0
     for rank, err in res:
         assert err is None, f"rank {rank}: {err}"
+
+
+def _empty_share_worker(rank, world, port, q):
+    """Exact sharding when a rank owns NO row of a global minibatch: it must contribute a zero gradient through the same
+    sequence of collectives (same buckets, same order) as the ranks that ran a backward pass - a mismatch dead-locks NCCL
+    (seen at 8 ranks x 4 rows) and corrupts gloo.  Checked against a one-process replay of the concatenated envs."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace as NS
+    from gail_carla_b200 import _abi
+    from oracle import abi_emu
+    for name in dir(abi_emu):
+        fn = getattr(abi_emu, name)
+        if callable(fn) and not name.startswith("_") and hasattr(_abi, name) and name not in ("call", "load_library"):
+            setattr(_abi, name, fn)
+    _abi.EMULATED = True
+    import gail_carla_b200 as G
+    from gail_carla_b200 import synthetic, optim
+    from gail_carla_b200.driver import update_iteration
+    import test_host_cpu as H
+    torch.set_num_threads(2)
+    T, Nl, Bglob = 3, 1, 2
+    N = Nl * world
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+
+    def build(mb):
+        torch.manual_seed(5)
+        pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, H.HP["logstd"], False)
+        agent = G.PPO(pol, H.HP["clip_param"], 2, mb, H.HP["value_loss_coef"], "cpu", lr=H.HP["lr"], eps=H.HP["eps"], betas=H.HP["betas"],
+                      max_grad_norm=H.HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+        disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, "cpu", H.HP["gail_lr"], H.HP["gail_eps"], H.HP["gail_betas"],
+                               H.HP["gail_max_grad_norm"])
+        return pol, agent, disc
+
+    full = G.RolloutStorage(T, N, synthetic.OBS_SHAPE, (4,), (2,), device="cpu")
+    synthetic.fill_rollout(full, seed=17)
+    loader = synthetic.SyntheticExpertLoader(3, Bglob, seed=23)
+    keys = ("obs", "metrics", "actions", "action_log_probs", "value_preds", "returns", "masks", "gail_rewards", "rewards")
+    # how many (rank, minibatch) shares are empty under the seed used below?  (same draws as the sharded run will make)
+    torch.manual_seed(99)
+    empties = 0
+    probe = G.RolloutStorage(T, Nl, (1, 2, 2), (4,), (2,), device="cpu"); probe.set_shard(rank, world)
+    for _ in range(3):                                   # compute_loss-free run: critic epoch, 2 PPO epochs
+        empties += sum(int(pos.numel() == 0) for pos, _ in probe.sharded_minibatches(Bglob))
+    pol, agent, disc = build(Bglob // world)
+    agent.exact_sharding = disc.exact_sharding = True
+    ro = G.RolloutStorage(T, Nl, synthetic.OBS_SHAPE, (4,), (2,), device="cpu")
+    for k in keys:
+        getattr(ro, k).copy_(getattr(full, k)[:, rank * Nl:(rank + 1) * Nl])
+    ro.set_shard(rank, world)
+    torch.manual_seed(99)
+    d_out, p_out = update_iteration(pol, agent, disc, ro, loader, gamma=0.99, gae_lambda=0.95, gail_epoch=1)
+    with optim.single_process():
+        pol1, agent1, disc1 = build(Bglob)
+        torch.manual_seed(99)
+        d1, p1 = update_iteration(pol1, agent1, disc1, full, loader, gamma=0.99, gae_lambda=0.95, gail_epoch=1)
+    err = None
+    try:
+        for (k, a), (_, b) in zip(list(pol.state_dict().items()) + list(disc.state_dict().items()),
+                                  list(pol1.state_dict().items()) + list(disc1.state_dict().items())):
+            assert torch.allclose(a, b, rtol=1e-4, atol=2e-6), f"{k}: max abs diff {(a - b).abs().max().item():.3g}"
+        assert torch.allclose(torch.tensor(d_out[0]), torch.tensor(d1[0]), rtol=1e-4, atol=1e-6)
+        assert torch.allclose(torch.tensor([x for x in p_out if x is not None]), torch.tensor([x for x in p1 if x is not None]),
+                              rtol=1e-4, atol=1e-6)
+    except AssertionError as ex:
+        err = str(ex)[:500]
+    q.put((rank, err, empties))
+    dist.destroy_process_group()
+
+
+def test_exact_sharding_with_empty_rank_shares():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_empty_share_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sum(e for _, _, e in res) > 0, "the seed no longer produces an empty share - pick another one"
+    for rank, err, _ in res:
+        assert err is None, f"rank {rank}: {err}"
