@@ -53,6 +53,7 @@ _SIGNATURES = {
     "gc_unprep_conv_wgrad": [_P, _I, _P, _P, _I, _I, _I, _P],
     "gc_prep_fc1_weight": [_P, _P, _I, _I, _L, _P],
     "gc_unprep_fc1_wgrad": [_P, _I, _P, _I, _I, _L, _P],
+    "gc_zero_block": [_P, _L, _L, _L, _P],
     "gc_grad_sumsq": [_P, _L, _F, _P, _P],
     "gc_clip_adam": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P, _P],
     "gc_conv_fprop": [_G, _P, _P, _P, _P, _P, _P, _I, _F, _P],
@@ -266,7 +267,18 @@ def unprep_fc1_wgrad(part, splits, dw, out, tail, ld):
     call("gc_unprep_fc1_wgrad", _ptr(part), splits, _ptr(dw), out, tail, ld, _stream())
 
 
+def zero_block(t: torch.Tensor, rows: int = 1, width: int = None, pitch: int = None):
+    """Zero `rows` runs of `width` elements of `t` that start `pitch` elements apart (default: the whole contiguous tensor)."""
+    if not t.is_cuda:
+        raise RuntimeError("gail_carla_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    es = t.element_size()
+    width = t.numel() if width is None else width
+    pitch = width if pitch is None else pitch
+    call("gc_zero_block", t.data_ptr(), pitch * es, rows, width * es, _stream())
+
+
 def grad_sumsq(grad, n, sumsq, grad_scale=1.0):
+    """sumsq[0] = sum (grad_scale * g)^2 (cleared first)."""
     call("gc_grad_sumsq", _ptr(grad), n, float(grad_scale), _ptr(sumsq, torch.float64), _stream())
 
 

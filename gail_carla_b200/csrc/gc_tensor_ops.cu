@@ -678,9 +678,16 @@ int gc_unprep_fc1_wgrad(const float* part, int splits, float* dw, int out, int t
   return gc::launch_status("unprep_fc1_kernel");
 }
 
+int gc_zero_block(void* ptr, long pitch_bytes, long rows, long width_bytes, void* stream) {
+  GC_REQUIRE(ptr && rows > 0 && width_bytes > 0 && pitch_bytes >= width_bytes, "gc_zero_block: bad arguments");
+  GC_CUDA_OK(cudaMemset2DAsync(ptr, (size_t)pitch_bytes, 0, (size_t)width_bytes, (size_t)rows, (cudaStream_t)stream));
+  return 0;
+}
+
 int gc_grad_sumsq(const float* grad, long n, float grad_scale, double* sumsq, void* stream) {
   GC_REQUIRE(grad && sumsq && n > 0, "gc_grad_sumsq: bad arguments");
   GC_REQUIRE(((uintptr_t)grad & 15) == 0, "gc_grad_sumsq: grad must be 16-byte aligned");
+  GC_CUDA_OK(cudaMemsetAsync(sumsq, 0, sizeof(double), (cudaStream_t)stream));
   grad_sumsq_kernel<<<grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(grad, n, grad_scale, sumsq);
   return gc::launch_status("grad_sumsq_kernel");
 }

@@ -158,8 +158,7 @@ class FusedClipAdam(torch.optim.Optimizer):
             self.t += 1
         b1, b2 = g["betas"]
         if self.max_grad_norm is not None:
-            self._sumsq.zero_()
-            A.grad_sumsq(flat.grad, n, self._sumsq, scale)
+            A.grad_sumsq(flat.grad, n, self._sumsq, scale)      # (clears the accumulator on the stream first)
         A.clip_adam(flat.flat, flat.grad, self._m, self._v, n, self._sumsq, self.max_grad_norm, float(g["lr"]), float(b1),
                     float(b2), float(g["eps"]), 1.0 - b1 ** max(self.t, 1), 1.0 - b2 ** max(self.t, 1), scale, True,
                     self.device_hyper(flat) if from_device_hyper else None)

@@ -59,7 +59,7 @@ class PPO():
         self.optimizer.grad_scale = 1.0 if exact else None
 
         # advantage statistics over the whole rollout (algo/ppo.py:47-49); normalisation itself is fused into the loss
-        stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        stats = torch.empty(4, dtype=torch.float64, device=dev)      # {sum, sumsq, count} are written by the kernel call
         A.adv_stats(rollouts.returns, rollouts.value_preds, stats, T * N)
         if world > 1:
             dist.all_reduce(stats[:3], op=dist.ReduceOp.SUM)   # {sum, sumsq, count} are additive across env shards
@@ -82,9 +82,9 @@ class PPO():
             self._dev_state[(B, str(dev))] = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev),
                                               torch.zeros(B, dtype=torch.int64, device=dev))
         acc, stats_buf, idx_buf = self._dev_state[(B, str(dev))]
+        A.zero_block(acc)
         if not eng.flat.grad_clean:        # a replayed step assumes the zeroed gradient buffer the previous step left behind
             eng.flat.grad.zero_(); eng.flat.grad_clean = True
-        acc.zero_()
         stats_buf.copy_(stats)
         opt = self.optimizer
         n_sched = self.ppo_epoch * ((T * N * (world if exact else 1)) // Bg)

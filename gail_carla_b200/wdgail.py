@@ -157,7 +157,7 @@ class CriticEngine:
         self.conv.input_grad(ws, B, 2 * B)
         A.grad_penalty(dA[0][2 * B:], ws.X0[2 * B:], acc[4:], B, S2D_PER_SAMPLE, lambda_, E.INV_STD, norm)
         self.conv.forward_masked(ws, B, 2 * B)
-        ws.F[2 * B:R, E.FEAT:].zero_()                                     # penalty gradient of the tail columns is 0
+        A.zero_block(ws.F[2 * B:, E.FEAT:], rows=B, width=LDF - E.FEAT, pitch=LDF)   # penalty gradient of the tail columns is 0
         t = ws.buf("v5", ws.rows, LDH)
         E.linear_fwd(ws, "fc1v", ws.F[2 * B:], LDF, self.w1, LDF, None, t, LDH, B, H_, LDF, EPI_STORE)
         A.splitk_reduce(t, 1, B, H_, LDH, None, H[2 * B:], LDH, t, LDH, EPI_MASK, E.SLOPE)
@@ -412,7 +412,7 @@ class Discriminator(nn.Module):
         if (B, str(dev)) not in self._alpha_buf:
             self._alpha_buf[(B, str(dev))] = (torch.zeros(8, dtype=torch.float64, device=dev), torch.zeros(B, device=dev))
         acc, alpha_buf = self._alpha_buf[(B, str(dev))]
-        acc.zero_()
+        A.zero_block(acc)
         if not eng.flat.grad_clean:        # a replayed step assumes the zeroed gradient buffer the previous step left behind
             eng.flat.grad.zero_(); eng.flat.grad_clean = True
 
@@ -519,12 +519,11 @@ class Discriminator(nn.Module):
         T, N = rollouts.num_steps, rollouts.num_processes
         obs_rows, met_rows, act_rows = rollouts.flat("obs"), rollouts.flat("metrics"), rollouts.flat("actions")
         out = rollouts.gail_rewards.view(-1)
-        idx_all = torch.arange(T * N, device=self._dev())
         with torch.no_grad():
             for s in range(0, T * N, chunk):
                 B = min(chunk, T * N - s)
                 eng.workspace(B)
-                eng.load_inputs(obs_rows, met_rows, act_rows, idx_all[s:s + B], B, 0)
+                eng.load_inputs(obs_rows[s:], met_rows[s:], act_rows[s:], None, B, 0)     # consecutive rows: no index vector
                 eng.tail_features(B, 0)
                 d = eng.forward(B)
                 A.reward_epilogue(d, out[s:], B)

@@ -155,7 +155,12 @@ int gc_unprep_fc1_wgrad(const float* part, int splits, float* dw, int out, int t
 /* ------------------------------------------------------------------------------------------------------------
  * Optimiser: clip_grad_norm_ + Adam - algo/ppo.py:115-119, algo/wdgail.py:140-145
  * ---------------------------------------------------------------------------------------------------------- */
-/* sumsq double[1] += sum (grad_scale*g)^2.  grad_scale = 1/world_size after a NCCL SUM all-reduce of per-rank mean
+/* Zero `rows` runs of `width_bytes` bytes that start `pitch_bytes` apart (a memset node on the stream, no kernel): loss
+ * accumulators, the metric / action columns of the gradient-penalty rows of the feature matrix (algo/wdgail.py:85-91 takes
+ * the gradient w.r.t. the image only). */
+int gc_zero_block(void* ptr, long pitch_bytes, long rows, long width_bytes, void* stream);
+
+/* sumsq double[1] = sum (grad_scale*g)^2 (the accumulator is cleared on the stream first).  grad_scale = 1/world_size after a NCCL SUM all-reduce of per-rank mean
  * gradients (the global-batch gradient of algo/ppo.py:115), 1 otherwise. */
 int gc_grad_sumsq(const float* grad, long n, float grad_scale, double* sumsq, void* stream);
 /* g' = grad_scale*g * min(1, max_norm/(sqrt(sumsq)+1e-6)); Adam step with g' (torch.optim.Adam, no amsgrad/weight decay).

@@ -304,8 +304,14 @@ def unprep_fc1_wgrad(part, splits, dw, out, tail, ld):
     d[:, 25600:] = s[:, 25600:25600 + tail]
 
 
+def zero_block(t, rows=1, width=None, pitch=None):
+    width = t.numel() if width is None else width
+    pitch = width if pitch is None else pitch
+    _v(t, (rows, width), (pitch, 1)).zero_()
+
+
 def grad_sumsq(grad, n, sumsq, grad_scale=1.0):
-    sumsq[0] += ((grad.reshape(-1)[:n].double() * grad_scale) ** 2).sum()
+    sumsq[0] = ((grad.reshape(-1)[:n].double() * grad_scale) ** 2).sum()
 
 
 def clip_adam(param, grad, exp_avg, exp_avg_sq, n, sumsq, max_norm, lr, beta1, beta2, eps, bc1, bc2, grad_scale=1.0,
