@@ -291,7 +291,10 @@ class Discriminator(nn.Module):
         on a side stream into a ring of three preallocated device staging sets, so the copies of batches i+1 and i+2 run
         while batch i is being processed (two batches of slack: other host->device traffic - a rollout streaming in for
         the next iteration - shares the DMA queue and would otherwise stall a minibatch every time it gets in front);
-        ``release()`` (called once the batch has been gathered into the workspace) lets the copy stream reuse that set."""
+        ``release()`` (called once the batch has been gathered into the workspace) lets the copy stream reuse that set.
+        The copies only overlap compute when the host tensors are PINNED (``DataLoader(pin_memory=True)``,
+        ``SyntheticExpertLoader(pin=True)``); CUDA copies pageable tensors synchronously with the host, which is correct but
+        serialises the upload with the enqueueing of the step.  A device-resident table (``DeviceExpertLoader``) needs no copy."""
         dev = self._dev()
         if dev.type != "cuda":
             for batch, idx in pairs:
