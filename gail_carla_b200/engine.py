@@ -101,14 +101,30 @@ class FlatParams:
         """True while every parameter is still a view of the flat buffer (``.to()`` / ``.cpu()`` break that)."""
         base = self.flat.data_ptr()
         for n, p in self.module.named_parameters():
-            if p.data_ptr() != base + 4 * self.offsets[n] or p.grad is None or p.device != self.flat.device:
+            if p.data_ptr() != base + 4 * self.offsets[n] or p.device != self.flat.device:
                 return False
         return True
+
+    def restore_grads(self) -> None:
+        """Re-attach ``p.grad`` to the flat gradient buffer.  A stock ``torch.optim`` optimiser's ``zero_grad()`` sets the
+        gradients to ``None`` (set_to_none=True is the default); None means zero, a foreign tensor is copied in."""
+        base = self.grad.data_ptr()
+        for n, p in self.module.named_parameters():
+            o = self.offsets[n]
+            if p.grad is None or p.grad.data_ptr() != base + 4 * o:
+                view = self.grad[o:o + p.numel()].view(p.shape)
+                if p.grad is None:
+                    view.zero_()
+                else:
+                    view.copy_(p.grad)
+                    self.grad_clean = False
+                p.grad = view
 
     def ensure(self) -> bool:
         if not self.ok():
             self.rebuild()
             return True
+        self.restore_grads()
         return False
 
     def g(self, name: str) -> torch.Tensor:

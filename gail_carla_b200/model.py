@@ -324,6 +324,7 @@ class _EvaluateActions(torch.autograd.Function):
             if g_value is not None:
                 d_head[:B, 0:1].copy_(g_value.reshape(B, 1))
             flat = eng.flat
+            flat.restore_grads()          # (a torch optimiser's zero_grad() sets p.grad to None)
             keep = None if flat.grad_clean else flat.grad.clone()
             eng.backward(B, d_head)
             grads = tuple(p.grad.clone() if p.requires_grad else None for p in policy.parameters())

@@ -1,0 +1,70 @@
+"""The training loop (gail_carla_b200/learn.py::gail_learning) against the scalar stream of the UNMODIFIED reference loop
+(tools/learn.py::gailLearning_mujoco_origin run by tests/golden/make_learn_golden.py on the same synthetic envs, seeds and
+hyper-parameters): same titles in the same order with the same step numbers, values within `tol`."""
+import json
+import math
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+
+HP = dict(lr=1e-4, eps=1e-8, betas=(0.9, 0.99), clip_param=0.1, value_loss_coef=0.5, max_grad_norm=0.5,
+          gail_lr=2.5e-4, gail_eps=1e-8, gail_betas=(0.9, 0.99), gail_max_grad_norm=0.5, gamma=0.99, gae_lambda=0.95,
+          logstd=[-1.4, -3.2])
+EXACT = ("Train steps", "Eval steps", "steer_std", "throttle_std", "ppo_entropy", "bc_loss", "Train reward", "Eval reward",
+         "route_00_max_reward", "route_00_min_reward")
+
+
+class Recorder:
+    def __init__(self):
+        self.rows = []
+
+    def add_scalar(self, title, value, step):
+        self.rows.append([str(title), float(value), int(step)])
+
+
+def run(device, tmp_path, tag):
+    import gail_carla_b200 as G
+    from gail_carla_b200 import learn as L, synthetic
+    gold = json.load(open(os.path.join(GOLDEN, "learn_loop.json")))
+    c = gold["case"]
+    torch.manual_seed(1); np.random.seed(1)
+    sp, asp = NS(shape=(4,)), NS(shape=(2,))
+    pol = G.Policy(synthetic.OBS_SHAPE, sp, asp, True, HP["logstd"], False)
+    agent = G.PPO(pol, HP["clip_param"], 1, c["B"], HP["value_loss_coef"], device, lr=HP["lr"], eps=HP["eps"], betas=HP["betas"],
+                  max_grad_norm=HP["max_grad_norm"], gamma=None, decay=None, act_space=asp)
+    disc = G.Discriminator(synthetic.OBS_SHAPE, sp, asp, 100, device, HP["gail_lr"], HP["gail_eps"], HP["gail_betas"],
+                           HP["gail_max_grad_norm"])
+    envs = synthetic.SyntheticVecEnv(c["nenv"], seed=3, device="cpu", mean_episode_len=c["mean_episode_len"], routes=(0,))
+    env_eval = synthetic.SyntheticEvalEnv(ep_length=c["eval_len"], seed=5, device="cpu")
+    train = synthetic.SyntheticExpertLoader(c["n_train"], c["B"], seed=21)
+    val = synthetic.SyntheticExpertLoader(c["n_val"], c["B"], seed=22)
+    rp = dict(num_steps=c["nsteps"], num_env_steps=c["updates"] * c["nsteps"], envs_params=[{}] * c["nenv"], routes=[0], lr=HP["lr"],
+              use_linear_lr_decay=True, gail_epoch=1, gail_pre_epoch=1, gail_thre=0, gamma=HP["gamma"], gae_lambda=HP["gae_lambda"],
+              bcgail=False, eval_interval=1, log_interval=1, resume_training=False)
+    rec = Recorder()
+    torch.manual_seed(7)
+    L.gail_learning(rp, envs, env_eval, pol, agent, disc, train, val, device, writer=rec, model_path=str(tmp_path / f"{tag}.pt"))
+    ckpt = torch.load(str(tmp_path / f"{tag}.pt"), map_location="cpu")
+    return gold, rec.rows, ckpt
+
+
+def check(gold, rows, ckpt, tol):
+    ref = gold["scalars"]
+    assert [(t, s) for t, _, s in rows] == [(t, s) for t, _, s in ref], "scalar titles / order / step numbers differ from the reference loop"
+    worst = 0.0
+    for (t, v, s), (_, r, _) in zip(rows, ref):
+        if r is None:
+            assert math.isnan(v), (t, s, v)
+            continue
+        lim = 1e-6 * (1 + abs(r)) if t in EXACT else tol * abs(r) + tol
+        assert abs(v - r) <= lim, f"{t} @ update {s}: {v} vs reference {r}"
+        if t not in EXACT:
+            worst = max(worst, abs(v - r) / (abs(r) + 1.0))
+    assert int(ckpt[2]) == gold["checkpoint_update"]
+    ps = float(sum(v.double().sum() for v in ckpt[0].values())); ds = float(sum(v.double().sum() for v in ckpt[1].values()))
+    assert abs(ps - gold["policy_param_sum"]) <= 0.5 and abs(ds - gold["disc_param_sum"]) <= 0.5     # Adam moved 1.4e7 / 3.3e6 parameters by <= lr each
+    return worst

@@ -114,3 +114,13 @@ def test_training_loop_runs_and_checkpoints(emulated_abi, tmp_path):
     rp2 = dict(rp, resume_training=True)
     log2 = L.gail_learning(rp2, envs, env_eval, pol2, agent, disc2, train, val, "cpu", model_path=path)
     assert log2.history == []
+
+
+def test_training_loop_matches_the_unmodified_reference_loop(emulated_abi, tmp_path):
+    """tools/learn.py::gailLearning_mujoco_origin (run unmodified by tests/golden/make_learn_golden.py with stand-ins only for
+    the tensorboardX / CARLA-client imports) vs gail_learning on the CPU statements of the ABI: the same scalar stream - titles,
+    order, step numbers - with values at fp32 re-association level (2e-3; the env-driven scalars exactly)."""
+    import learn_cases as LC
+    gold, rows, ckpt = LC.run("cpu", tmp_path, "cpu")
+    worst = LC.check(gold, rows, ckpt, tol=2e-3)
+    print("worst relative deviation from the reference loop:", worst)

@@ -63,6 +63,15 @@ def test_learn_loop_gpu_matches_cpu_statement(tmp_path, monkeypatch):
                 assert abs(a[k] - b[k]) <= 5e-2 * abs(b[k]) + 5e-2, (k, a[k], b[k])
 
 
+def test_training_loop_gpu_matches_the_unmodified_reference_loop(tmp_path):
+    """The GPU run of the whole loop against the scalar stream of the unmodified reference loop (tests/golden/learn_loop.json):
+    same titles / order / steps; values within 5e-2 relative + 5e-2 absolute (TF32 contractions, 16-row minibatches, Adam's
+    sign-like first steps - see tests/test_update_gpu.py for the per-update bar)."""
+    import learn_cases as LC
+    gold, rows, ckpt = LC.run("cuda", tmp_path, "gpu")
+    LC.check(gold, rows, ckpt, tol=5e-2)
+
+
 def test_learn_bc_gpu_matches_cpu_statement(tmp_path, monkeypatch):
     """learn_bc.py:15-72 on the device-resident expert table: GPU (TF32 trunk) vs the CPU statement of the ABI from the
     same seeds.  The BC loss is -log N(a; mu, sigma) with sigma = e^-3.2 = 0.04, i.e. (a-mu)^2 is amplified ~300x, and
