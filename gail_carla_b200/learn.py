@@ -158,8 +158,11 @@ def evaluation_episode(env_eval, actor_critic, rollout_eval: RolloutStorage):
 
 
 def gail_learning(run_params: dict, envs, env_eval, actor_critic, agent, discriminator, gail_train_loader, gail_val_loader,
-                  device, writer=None, model_path: str = "gail_model.pt", verbose: bool = False) -> ScalarLog:
-    """The loop of tools/learn.py ``gailLearning_mujoco_origin``; returns the scalar log."""
+                  device, writer=None, model_path: str = "gail_model.pt", verbose: bool = False,
+                  obs_dtype=torch.float32) -> ScalarLog:
+    """The loop of tools/learn.py ``gailLearning_mujoco_origin``; returns the scalar log.
+    ``obs_dtype=torch.uint8`` keeps the rollout observations in the byte store (storage.ByteObs; lossless for the simulator's
+    uint8/255 observations, off-grid values raise)."""
     log = ScalarLog(writer)
     if torch.device(device).type == "cuda" and torch.device(device).index is not None:
         torch.cuda.set_device(torch.device(device))     # kernels and streams are issued on the current device
@@ -167,7 +170,7 @@ def gail_learning(run_params: dict, envs, env_eval, actor_critic, agent, discrim
     nbatch = int(math.floor(run_params["num_steps"] / nenv))
     nupdates = int(math.floor(run_params["num_env_steps"] / run_params["num_steps"]))
     rollouts = RolloutStorage(nbatch, nenv, envs.observation_space.shape, envs.metrics_space.shape, envs.action_space.shape,
-                              device=device)
+                              device=device, obs_dtype=obs_dtype)
     rollout_eval = None
     if env_eval is not None:
         rollout_eval = RolloutStorage(env_eval.ep_length, 1, envs.observation_space.shape, envs.metrics_space.shape,

@@ -26,7 +26,7 @@ class Recorder:
         self.rows.append([str(title), float(value), int(step)])
 
 
-def run(device, tmp_path, tag):
+def run(device, tmp_path, tag, obs_dtype=torch.float32):
     import gail_carla_b200 as G
     from gail_carla_b200 import learn as L, synthetic
     gold = json.load(open(os.path.join(GOLDEN, "learn_loop.json")))
@@ -47,7 +47,8 @@ def run(device, tmp_path, tag):
               bcgail=False, eval_interval=1, log_interval=1, resume_training=False)
     rec = Recorder()
     torch.manual_seed(7)
-    L.gail_learning(rp, envs, env_eval, pol, agent, disc, train, val, device, writer=rec, model_path=str(tmp_path / f"{tag}.pt"))
+    L.gail_learning(rp, envs, env_eval, pol, agent, disc, train, val, device, writer=rec, model_path=str(tmp_path / f"{tag}.pt"),
+                    obs_dtype=obs_dtype)
     ckpt = torch.load(str(tmp_path / f"{tag}.pt"), map_location="cpu")
     return gold, rec.rows, ckpt
 

@@ -124,3 +124,11 @@ def test_training_loop_matches_the_unmodified_reference_loop(emulated_abi, tmp_p
     gold, rows, ckpt = LC.run("cpu", tmp_path, "cpu")
     worst = LC.check(gold, rows, ckpt, tol=2e-3)
     print("worst relative deviation from the reference loop:", worst)
+
+
+def test_training_loop_on_the_byte_store_matches_the_reference_loop(emulated_abi, tmp_path):
+    """Same run with the rollout in the uint8 observation store (insert / act / predict_reward / update all on ByteObs):
+    lossless, so the same golden at the same tolerance."""
+    import learn_cases as LC
+    gold, rows, ckpt = LC.run("cpu", tmp_path, "cpu_u8", obs_dtype=torch.uint8)
+    LC.check(gold, rows, ckpt, tol=2e-3)
