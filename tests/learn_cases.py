@@ -14,8 +14,10 @@ from conftest import GOLDEN
 HP = dict(lr=1e-4, eps=1e-8, betas=(0.9, 0.99), clip_param=0.1, value_loss_coef=0.5, max_grad_norm=0.5,
           gail_lr=2.5e-4, gail_eps=1e-8, gail_betas=(0.9, 0.99), gail_max_grad_norm=0.5, gamma=0.99, gae_lambda=0.95,
           logstd=[-1.4, -3.2])
-EXACT = ("Train steps", "Eval steps", "steer_std", "throttle_std", "ppo_entropy", "bc_loss", "Train reward", "Eval reward",
-         "route_00_max_reward", "route_00_min_reward")
+EXACT = ("Train steps", "Eval steps", "steer_std", "throttle_std", "ppo_entropy", "bc_loss")
+# env-driven scalars: the synthetic env's reward is -steer^2 of the policy's action, so they are exact only when the policy
+# forward is fp32 (CPU statements); on the GPU they carry the TF32 deviation of the action mean (observed 6e-4 relative)
+ENV_DRIVEN = ("Train reward", "Eval reward", "route_00_max_reward", "route_00_min_reward")
 
 
 class Recorder:
@@ -53,7 +55,7 @@ def run(device, tmp_path, tag, obs_dtype=torch.float32):
     return gold, rec.rows, ckpt
 
 
-def check(gold, rows, ckpt, tol):
+def check(gold, rows, ckpt, tol, exact_env=True):
     ref = gold["scalars"]
     assert [(t, s) for t, _, s in rows] == [(t, s) for t, _, s in ref], "scalar titles / order / step numbers differ from the reference loop"
     worst = 0.0
@@ -61,9 +63,10 @@ def check(gold, rows, ckpt, tol):
         if r is None:
             assert math.isnan(v), (t, s, v)
             continue
-        lim = 1e-6 * (1 + abs(r)) if t in EXACT else tol * abs(r) + tol
+        exact = t in EXACT or (exact_env and t in ENV_DRIVEN)
+        lim = 1e-6 * (1 + abs(r)) if exact else tol * abs(r) + tol
         assert abs(v - r) <= lim, f"{t} @ update {s}: {v} vs reference {r}"
-        if t not in EXACT:
+        if not exact:
             worst = max(worst, abs(v - r) / (abs(r) + 1.0))
     assert int(ckpt[2]) == gold["checkpoint_update"]
     ps = float(sum(v.double().sum() for v in ckpt[0].values())); ds = float(sum(v.double().sum() for v in ckpt[1].values()))

@@ -69,7 +69,7 @@ def test_training_loop_gpu_matches_the_unmodified_reference_loop(tmp_path):
     sign-like first steps - see tests/test_update_gpu.py for the per-update bar)."""
     import learn_cases as LC
     gold, rows, ckpt = LC.run("cuda", tmp_path, "gpu")
-    LC.check(gold, rows, ckpt, tol=5e-2)
+    LC.check(gold, rows, ckpt, tol=5e-2, exact_env=False)
 
 
 def test_learn_bc_gpu_matches_cpu_statement(tmp_path, monkeypatch):
