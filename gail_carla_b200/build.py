@@ -23,6 +23,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "--expt-relaxed-constexpr"]
 
 
+def _flags():
+    """GC_UMMA_STATS_BUILD=1 compiles the per-role wait counters of the GEMM kernel in (GC_UMMA_STATS=1 then prints them);
+    the production build has no clock reads or counter updates in its loops."""
+    return NVCC_FLAGS + (["-DGC_UMMA_STATS_BUILD"] if os.environ.get("GC_UMMA_STATS_BUILD") else [])
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for f in SOURCES + HEADERS:
@@ -30,7 +36,7 @@ def _digest() -> str:
             h.update(fh.read())
     with open(os.path.join(INCLUDE, "gail_carla_b200.h"), "rb") as fh:
         h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -67,7 +73,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, f'-DGC_BUILD_DIGEST="{dig}"', "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *_flags(), f'-DGC_BUILD_DIGEST="{dig}"', "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -201,7 +201,11 @@ int finish_and_launch(Plan& pl, cudaStream_t st, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (e != cudaSuccess) return gc::fail((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
     static long long* d_stats = nullptr;   // debug only: GC_UMMA_STATS=1 prints where each role of the kernel waits
+#ifdef GC_UMMA_STATS_BUILD
     static const bool want_stats = getenv("GC_UMMA_STATS") != nullptr;
+#else
+    static const bool want_stats = false;   // counters are compiled out of the production kernel (build with GC_UMMA_STATS_BUILD=1)
+#endif
     if (want_stats) {
       if (!d_stats) cudaMalloc(&d_stats, gc::kNumSMs * 16 * sizeof(long long));
       cudaMemsetAsync(d_stats, 0, gc::kNumSMs * 16 * sizeof(long long), st);

@@ -337,7 +337,11 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
   const int total_tiles = p.mt * p.nt * p.zt;
   const int acc_cols = ((p.bn + 31) >> 5) << 5;
   const int acc_stages = p.acc_stages;
-  const bool timed = p.stats != nullptr;
+#ifdef GC_UMMA_STATS_BUILD
+  const bool timed = p.stats != nullptr;   // per-role wait counters (debug build only: python -m gail_carla_b200.build with GC_UMMA_STATS_BUILD=1)
+#else
+  constexpr bool timed = false;            // production build: the clock reads and counter updates are compiled out
+#endif
   const uint32_t pair_rank = CTA2 ? cluster_ctarank() : 0u;   // 0 = leader
 
   if (threadIdx.x == 0) {
@@ -644,13 +648,14 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const int r0 = row % p.row_box[0], r1 = (row / p.row_box[0]) % p.row_box[1], r2 = row / (p.row_box[0] * p.row_box[1]);
     int pf_tile = blockIdx.x, pf_q = 0, pf_count = 0;  // mask prefetch cursor (group leader only; single-group mode)
     // output panel q of a tile -> which tensor map and which coordinates
+    const int op_cpm = p.cols_per_map, op_sh = p.cpm_shift, op_off0 = p.d.off[0], op_bn = p.bn;
     auto out_panel = [&](const int (&base)[5], int n_tile, int q, int (&c)[5]) -> int {
-      if (p.cols_per_map > 0) {
-        const int col = n_tile * p.bn + q * 32;
+      if (op_cpm > 0) {
+        const int col = n_tile * op_bn + q * 32;
 #pragma unroll
         for (int d = 0; d < 5; ++d) c[d] = base[d];
-        c[0] = p.d.off[0] + (col & (p.cols_per_map - 1));   // cols_per_map is a power of two (host-checked)
-        return col >> p.cpm_shift;
+        c[0] = op_off0 + (col & (op_cpm - 1));   // cols_per_map is a power of two (host-checked)
+        return col >> op_sh;
       }
       if constexpr (SLAB) {
 #pragma unroll
@@ -707,6 +712,20 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
     const int sp1 = p.d.panel2[1], sp2 = p.d.panel2[2], sp3 = p.d.panel2[3];
     const long sub_words = (sp1 * bs0 + sp2 * bs1 + sp3 * bs2) >> 5;
     const uint32_t s_bias_u32 = smem_u32(s_bias), my_staging_u32 = smem_u32(my_staging);
+    // Everything the per-panel code needs from the kernel parameters lives in registers: an ncu source-level capture of conv1
+    // fprop (profiles/r02_ncu_conv1_fprop_bits_summary.txt) showed ~700 warp instructions per 128x32 panel of which ~150 were
+    // the epilogue's arithmetic - the rest were constant-bank reloads of these fields (LDC: 14 % of the stall samples), the
+    // q % period / q / period divisions of the panel walk (MUFU.RCP sequences) and the debug clock reads.
+    const int d_period = p.d.period, cpm = p.cols_per_map, cpm_sh = p.cpm_shift, d_off0 = p.d.off[0], tile_bn = p.bn,
+              n_total = p.n_total;
+    int dpan[5], dwrap[5];         // panel walk: + dpan per panel, + dwrap when the first level wraps (two-level walk)
+#pragma unroll
+    for (int d = 0; d < 5; ++d) {
+      dpan[d] = p.d.panel[d];
+      dwrap[d] = p.d.panel2[d] - (d_period > 0 ? d_period - 1 : 0) * p.d.panel[d];
+    }
+    unsigned* const bits_out = p.bits_out;
+    const unsigned* const bits_in = p.bits_in;
     int pc = 0, bi = 0;            // panels done so far, staging buffer of the current panel (pc % nbuf without the division)
     uint32_t bph = 0;              // (pc / nbuf) & 1
     long long w_tfull = 0, e_free = 0, e_ld = 0, e_math = 0, e_store = 0, e_sts = 0, e_bar = 0;
@@ -748,7 +767,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
           if (q < n_panels) {
             const long wi = bit_word(q);
             if (wi >= 0) {
-              mbits[q] = __ldg(p.bits_in + wi);
+              mbits[q] = __ldg(bits_in + wi);
               cs_ok |= in_limit ? (1u << q) : 0u;
             }
           }
@@ -757,10 +776,37 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
       mbar_wait_t(tfull0 + 8 * acc, aph, timed, w_tfull);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_cols);
+      int crun[5], q1 = 0;          // running panel coordinates of the plain / two-level panel walk (no division per panel)
+#pragma unroll
+      for (int d = 0; d < 5; ++d) crun[d] = cd[d];
+      int col0 = sub_panels > 0 ? 0 : n_tile * tile_bn, subq = 0;   // first channel of the current panel (bias index / column guard)
       for (int q = 0; q < n_panels; ++q, ++pc) {
         const uint32_t buf = my_staging_u32 + (uint32_t)bi * 16384u;
         int cq_st[5];   // store coordinates of this panel, formed before the barriers so the leader only has to issue
-        const int mi_st = out_panel(cd, n_tile, q, cq_st);
+        int mi_st = 0;
+        if (cpm > 0) {
+          const int col = n_tile * tile_bn + q * 32;
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cq_st[d] = cd[d];
+          cq_st[0] = d_off0 + (col & (cpm - 1));
+          mi_st = col >> cpm_sh;
+        } else if constexpr (SLAB) {
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cq_st[d] = cd[d];
+          cq_st[0] += p.panel_tab0[q];
+          cq_st[1] += p.panel_tab1[q];
+        } else {
+#pragma unroll
+          for (int d = 0; d < 5; ++d) cq_st[d] = crun[d];
+          if (d_period > 0 && ++q1 == d_period) {
+            q1 = 0;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) crun[d] += dwrap[d];
+          } else {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) crun[d] += dpan[d];
+          }
+        }
         const long long c0 = timed ? clock64() : 0;
         if (leader()) {
           if (two_groups) {
@@ -785,8 +831,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
           }
         }
-        // first channel of this panel (bias index / column guard): sub-tile mode repeats the channel panels per sub-tile
-        const int col0 = sub_panels > 0 ? (sub_panels == 1 ? 0 : (q % sub_panels) * 32) : n_tile * p.bn + q * 32;
+        // (col0: first channel of this panel; sub-tile mode repeats the channel panels per sub-tile)
         unsigned bits_w = 0u, bits4[4] = {0u, 0u, 0u, 0u};
         long bits_wi = -1;
         if (epi == EPI_BIAS_LRELU || epi == EPI_BIAS) {
@@ -798,7 +843,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < p.n_total) ? __ldg(p.bias + col0 + j) : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < n_total) ? __ldg(p.bias + col0 + j) : 0.f;
           }
           if (epi == EPI_BIAS_LRELU) {
             if (want_bits) {
@@ -822,7 +867,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         }
         if (want_bits) {
           unsigned w = (bits4[0] | bits4[1]) | (bits4[2] | bits4[3]);
-          if (col0 + 32 > p.n_total) w &= (1u << (p.n_total - col0)) - 1u;   // partial last panel
+          if (col0 + 32 > n_total) w &= (1u << (n_total - col0)) - 1u;   // partial last panel
           bits_w = w;
           if (simple_panels) {
             bits_wi = bw0 >= 0 ? bw0 + q : -1;
@@ -864,7 +909,7 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         epi_bar_sync(grp);
         const long long c3 = timed ? clock64() : 0;
         // the LeakyReLU' bit word goes out after the proxy fence so the fence never waits on a global store
-        if (bits_wi >= 0) p.bits_out[bits_wi] = bits_w;
+        if (bits_wi >= 0) bits_out[bits_wi] = bits_w;
         if (leader()) {
           tma_store_5d(&p.mapD[mi_st], buf, cq_st);
           tma_commit();
@@ -887,6 +932,8 @@ __global__ void __launch_bounds__(320, 1) umma_gemm_kernel(const __grid_constant
         }
         if (timed) { e_free += c1 - c0; e_ld += c2 - c1; e_math += c2a - c2; e_sts += c2b - c2a; e_bar += c3 - c2b; e_store += clock64() - c3; }
         if (++bi == nbuf) { bi = 0; bph ^= 1; }
+        if (sub_panels == 0) col0 += 32;
+        else if (sub_panels > 1) { col0 += 32; if (++subq == sub_panels) { subq = 0; col0 = 0; } }
       }
       if (two_groups) aph ^= 1;                                   // this group's stage is used by every other tile
       else if (++acc == acc_stages) { acc = 0; aph ^= 1; }
