@@ -274,6 +274,11 @@ __device__ __forceinline__ void track_init(CoordTrack& t, const TmaAddr& a, cons
   }
 }
 __device__ __forceinline__ void track_next(CoordTrack& t, unsigned carries) {
+  if (carries == 0u) {   // the common step (no digit wrapped): five additions instead of thirty select-adds (warp-uniform branch)
+#pragma unroll
+    for (int d = 0; d < 5; ++d) t.c[d] += t.base[d];
+    return;
+  }
 #pragma unroll
   for (int d = 0; d < 5; ++d) {
     int v = t.c[d] + t.base[d];
