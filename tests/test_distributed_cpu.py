@@ -165,7 +165,7 @@ def _empty_share_worker(rank, world, port, q):
     from gail_carla_b200.driver import update_iteration
     import test_host_cpu as H
     torch.set_num_threads(2)
-    T, Nl, Bglob = 3, 1, 2
+    T, Nl, Bglob = 3, 1, world     # one row per rank on average: empty shares are frequent
     N = Nl * world
     sp, asp = NS(shape=(4,)), NS(shape=(2,))
 
@@ -204,7 +204,9 @@ def _empty_share_worker(rank, world, port, q):
     try:
         for (k, a), (_, b) in zip(list(pol.state_dict().items()) + list(disc.state_dict().items()),
                                   list(pol1.state_dict().items()) + list(disc1.state_dict().items())):
-            assert torch.allclose(a, b, rtol=1e-4, atol=2e-6), f"{k}: max abs diff {(a - b).abs().max().item():.3g}"
+            # fp32 sums in a different order (per-rank partial gradients summed by the all-reduce vs one batch) move an Adam
+            # step by a small fraction of lr (1e-4 / 2.5e-4): 2e-5 absolute
+            assert torch.allclose(a, b, rtol=1e-4, atol=2e-5), f"{k}: max abs diff {(a - b).abs().max().item():.3g}"
         assert torch.allclose(torch.tensor(d_out[0]), torch.tensor(d1[0]), rtol=1e-4, atol=1e-6)
         assert torch.allclose(torch.tensor([x for x in p_out if x is not None]), torch.tensor([x for x in p1 if x is not None]),
                               rtol=1e-4, atol=1e-6)
@@ -214,11 +216,12 @@ def _empty_share_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_exact_sharding_with_empty_rank_shares():
+@pytest.mark.parametrize("world", [2, 4])
+def test_exact_sharding_with_empty_rank_shares(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 1000
-    procs = [ctx.Process(target=_empty_share_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 31500 + 7 * world + os.getpid() % 1000
+    procs = [ctx.Process(target=_empty_share_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
